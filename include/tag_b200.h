@@ -1,0 +1,170 @@
+/*
+ * tag_b200.h — C ABI of the B200-native TAG scoring hot path (libtag_b200.so).
+ *
+ * The reference (XThomasBU/video-gen-evals) is pure Python and has no FFI; the boundary it
+ * exposes is its Python call signatures. Each entry point below replaces the
+ * reference code cited next to it; the Python shim in `video-gen-evals_b200/` keeps the
+ * reference's names/arguments and calls these through ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer on the handle's device
+ *    unless marked HOST. The caller (PyTorch) owns all tensors; the library owns only the
+ *    opaque handle (packed weights + workspace allocated in tag_finalize_weights).
+ *  - all work is enqueued asynchronously on the cudaStream_t passed as `void* stream`.
+ *  - return 0 on success, a TAG_ERR_* code otherwise; tag_last_error() gives the message.
+ *    No exceptions or aborts cross the ABI. A handle is not thread-safe.
+ *  - all floating point tensors are fp32, row-major, densely packed.
+ */
+#ifndef TAG_B200_H
+#define TAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAG_MAX_MODALITIES 8
+#define TAG_D_MODEL 256
+
+enum {
+  TAG_OK = 0,
+  TAG_ERR_INVALID = 1,      /* bad argument / unsupported configuration */
+  TAG_ERR_CUDA = 2,         /* a CUDA runtime/driver call failed        */
+  TAG_ERR_STATE = 3,        /* call order (weights not finalized, ...)  */
+  TAG_ERR_MISSING = 4,      /* a required weight was never loaded       */
+  TAG_ERR_UNSUPPORTED = 5   /* device is not sm_100 / shape not covered */
+};
+
+/* how a modality's frame-to-frame delta is formed (reference utils.py:142-217, :455-470) */
+enum {
+  TAG_KIND_COSINE = 0,      /* vit / clip / dino: L2-normalise, first difference  (_vit_delta  :142-147) */
+  TAG_KIND_ROTMAT = 1,      /* global / pose: J 3x3 matrices -> log(R_prev^T R)   (_rotmat_delta :165-174) */
+  TAG_KIND_PLAIN = 2,       /* betas: first difference                             (_betas_delta :161-163) */
+  TAG_KIND_PROCRUSTES = 3   /* kp2d: centre, scale, rotate-align, difference       (_procrustes_kp_delta :177-217) */
+};
+
+enum {
+  TAG_PRECISION_FP32 = 0,   /* fp32 CUDA-core GEMMs: reference-precision mode                     */
+  TAG_PRECISION_FP16_TC = 1 /* fp16 operands, fp32 accumulate on tcgen05 tensor cores (default)   */
+};
+
+typedef struct tag_handle tag_handle;
+
+/* mirrors HumanActionScorer.__init__ (reference model.py:103-146) */
+typedef struct tag_config {
+  int32_t n_modalities;                       /* M, in concat order (utils.py:496-510)          */
+  int32_t raw_dims[TAG_MAX_MODALITIES];       /* dims_map_raw  values                           */
+  int32_t diff_dims[TAG_MAX_MODALITIES];      /* dims_map_diff values (0 = no motion encoder)   */
+  int32_t kinds[TAG_MAX_MODALITIES];          /* TAG_KIND_* per modality (used by feature fuse) */
+  int32_t d_model;                            /* 256 (only value supported)                     */
+  int32_t n_heads;                            /* 8   (head_dim must be 32)                      */
+  int32_t n_layers;                           /* temporal transformer layers (4)                */
+  int32_t ffn_dim;                            /* 4*d_model                                      */
+  int32_t n_blocks;                           /* conv blocks per encoder, dilation 2^b (4)      */
+  int32_t conv_kernel;                        /* 5                                              */
+  int32_t precision;                          /* TAG_PRECISION_*                                */
+  int32_t max_windows;                        /* windows per internal pass (workspace size)     */
+  int32_t max_T;                              /* largest clip_len that will be passed           */
+  int32_t device;                             /* CUDA device ordinal                            */
+} tag_config;
+
+/* per-modality packed frame arrays of V videos (what extract_mesh.py:25-44 / DWpose emit),
+ * frames of video v are rows frame_offset[v] .. frame_offset[v+1]-1 of every array */
+typedef struct tag_videos {
+  const float* src[TAG_MAX_MODALITIES];       /* [F, raw_dims[m]] each                          */
+  const int64_t* frame_offset;                /* [V+1]                                          */
+  int64_t n_videos;
+} tag_videos;
+
+/* --- lifetime ---------------------------------------------------------------------------- */
+int tag_create(tag_handle** out, const tag_config* cfg);
+void tag_destroy(tag_handle* h);
+const char* tag_last_error(const tag_handle* h);   /* h may be NULL: last error of tag_create */
+int tag_abi_version(void);
+
+/* --- weights: reference eval.py:136-165 `load_model` / state_dict key contract -------------
+ * `key` is the reference state_dict key (e.g. "state_enc.vit.blocks.0.conv1.weight", with the
+ * modality NAME replaced by its index: "state_enc.0.blocks..."); data may be HOST or DEVICE. */
+int tag_load_weight(tag_handle* h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
+int tag_finalize_weights(tag_handle* h);
+
+/* --- K1 feature fuse: WindowDataset._try_one compute part (utils.py:366-381, :396-404,
+ *     :455-514): slice/pad, raw flatten, per-window deltas, z-score, concat [raw || diff].
+ *     mean/stdv: [D] in feats column order, NULL = no normalisation (stats=None path).
+ *     feats_out [n_windows, T, D]; flags_out[0] += #frames with det(H) < 0 (Procrustes
+ *     reflection regime, not reproducible in closed form — SURVEY.md §8a A6), nullable. */
+int tag_feature_fuse(tag_handle* h, const tag_videos* vids, const float* mean, const float* stdv,
+                     const int32_t* win_video, const int32_t* win_start, int64_t n_windows, int32_t T,
+                     float* feats_out, int32_t* flags_out, void* stream);
+
+/* --- K2 encoder: HumanActionScorer.forward (model.py:162-193). feats [n_windows, T, D].
+ *     outputs (any may be NULL except seq_embed): seq_embed [N,256], frame_embeds [N,T+1,256],
+ *     tokens [N,T+1,256]; tc_window [N] = per-window temporal coherence of eval.py:218-224
+ *     (fused, so frame_embeds need not leave the device). */
+int tag_encode(tag_handle* h, const float* feats, int64_t n_windows, int32_t T,
+               float* seq_embed, float* frame_embeds, float* tokens, float* tc_window, void* stream);
+
+/* --- K1+K2 fused over windows of resident videos: eval.py:168-206 `extract_window_features`
+ *     without materialising feats for all windows (internally chunked by max_windows). */
+int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean, const float* stdv,
+                       const int32_t* win_video, const int32_t* win_start, int64_t n_windows, int32_t T,
+                       float* seq_embed, float* frame_embeds, float* tokens, float* tc_window,
+                       int32_t* flags_out, void* stream);
+
+/* --- K3 centroids: build_train_centroids_subset (utils.py:1035-1043).
+ *     sums_counts [C, 257] (256 sums || count) is accumulated INTO (zero it first); it is the
+ *     buffer that is all-reduced across ranks before tag_centroid_finalize. labels int32 [n];
+ *     labels outside [0, C) are ignored. */
+int tag_centroid_accumulate(tag_handle* h, const float* z, const int32_t* labels, int64_t n, int32_t C,
+                            float* sums_counts, void* stream);
+int tag_centroid_finalize(tag_handle* h, const float* sums_counts, int32_t C, float* centroids,
+                          float* counts, void* stream);
+
+/* --- K4 scores: compute_action_consistency_scores (eval.py:235-255) and the per-video mean of
+ *     compute_temporal_coherence_scores (eval.py:226). Windows of video v are rows
+ *     seg_offsets[v] .. seg_offsets[v+1]-1. video_label outside [0, C) => ac_out = NaN (the
+ *     reference silently skips such videos, eval.py:247-251). tc_out of a video with no
+ *     windows (or T < 2) = NaN. tc_window may be NULL (then tc_out is not written); seq_embeds may
+ *     be NULL (then only the TC aggregation runs and video_label / centroids / ac_out are ignored). */
+int tag_score(tag_handle* h, const float* seq_embeds, const float* tc_window, const int64_t* seg_offsets,
+              const int32_t* video_label, const float* centroids, int32_t C, int64_t n_videos,
+              float* ac_out, float* tc_out, void* stream);
+
+/* --- per-window temporal coherence from ALREADY NORMALISED frame embeddings [N, S, 256] (S = T+1,
+ *     row 0 = CLS): mean_t ||f_{t+1} - f_t||_2 over the T-1 frame pairs (eval.py:218-224); NaN when
+ *     the window has fewer than 2 frames (the reference skips those). */
+int tag_window_tc(tag_handle* h, const float* frame_embeds, int64_t n_windows, int32_t S, float* tc_window, void* stream);
+
+/* --- N2 stats: per-column float64 sum / sum-of-squares of a [rows, D] fp32 matrix, accumulated
+ *     INTO sum/sumsq (compute_stats_from_npz, utils.py:589-593). */
+int tag_stats_accumulate(tag_handle* h, const float* x, int64_t rows, int32_t D, double* sum, double* sumsq,
+                         void* stream);
+
+/* --- N1 TCL forward (losses.py:14-34): per-row loss terms of the [B,B] similarity matrix in
+ *     one pass; loss_rows [B] (mean over rows = the reference's scalar). targets int32 [B]. */
+int tag_tcl_forward(tag_handle* h, const float* z, const int32_t* targets, int64_t B, float temperature,
+                    float k1, float k2, float* loss_rows, void* stream);
+
+/* --- introspection used by bench.py: kernels launched through this handle since creation; with
+ *     profiling on, every encoder kernel is bracketed by CUDA events on the caller's stream and
+ *     out9 = {other: ms, flops, launches | conv GEMM: ms, flops, launches | other GEMM: ms, flops,
+ *     launches}, accumulated since tag_set_profiling(h, 1). */
+int64_t tag_launch_count(const tag_handle* h);
+int tag_set_profiling(tag_handle* h, int32_t on);
+int tag_get_profile(tag_handle* h, double* out9);
+
+/* --- test hooks: the two GEMM kernels in isolation (tests/test_gemm_gpu.py).
+ *     C = act(sum_taps A[row+shift] W^T + bias + res); fp32: W [N, ldw]; tensor-core: A/W/res16/C16
+ *     are fp16, W [N, taps*K], ld of res/C = N. */
+int tag_debug_gemm_f32(tag_handle* h, const float* A, int32_t lda, const float* W, int32_t ldw, int64_t M, int32_t N,
+                       int32_t K, int32_t taps, int32_t dil, int32_t T, const float* bias, const float* res, float* C,
+                       int32_t act, void* stream);
+int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, int64_t M, int32_t N, int32_t K,
+                      int32_t taps, int32_t dil, int32_t T, const float* bias, const void* res16, const float* res32,
+                      void* C16, float* C32, int32_t act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAG_B200_H */

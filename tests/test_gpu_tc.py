@@ -1,0 +1,142 @@
+"""GPU tests of the tcgen05/TMA tensor-core path (pytest -m gpu): the GEMM kernel in isolation against a
+float64 reference of the same fp16-rounded operands, then the whole encoder in 'fp16_tc' mode against
+the reference goldens at the north-star tolerance (1e-3 relative on AC / TC / centroids)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import tag_b200 as tb
+from tag_b200 import _lib
+from helpers import golden_case, oracle, max_abs
+from test_gpu_kernels import _gemm_ref, _model, _check_scores
+
+pytestmark = pytest.mark.gpu
+O = oracle()
+DEV = "cuda:0"
+
+
+def _diag(got, ref, name):
+    """Human-readable mismatch report (layout bugs show up as structured error patterns)."""
+    err = (got.double() - ref).abs()
+    scale = max(1.0, ref.abs().max().item())
+    bad = err > 5e-3 * scale
+    lines = [f"{name}: max err {err.max().item():.3e} (scale {scale:.3e}), mismatched {bad.float().mean().item() * 100:.2f}%"]
+    if bad.any():
+        rows = bad.any(1).nonzero().flatten()
+        cols = bad.any(0).nonzero().flatten()
+        lines.append(f"  bad rows: n={rows.numel()} first={rows[:12].tolist()} last={rows[-4:].tolist()}")
+        lines.append(f"  bad cols: n={cols.numel()} first={cols[:12].tolist()} last={cols[-4:].tolist()}")
+        r0, c0 = rows[0].item(), cols[0].item()
+        lines.append(f"  got[{r0},{c0}:{c0 + 6}] = {got[r0, c0:c0 + 6].tolist()}")
+        lines.append(f"  ref[{r0},{c0}:{c0 + 6}] = {ref[r0, c0:c0 + 6].tolist()}")
+        # is the output a permutation of the reference rows? (swizzle / row-mapping bugs)
+        g0 = got[r0].double()
+        d = (ref - g0[None, :]).abs().max(1).values
+        lines.append(f"  got row {r0} is closest to ref row {d.argmin().item()} (err {d.min().item():.3e})")
+    return "\n".join(lines)
+
+
+def _run_tc(M, N, K, taps, dil, T, act, use_bias, res_kind, out_kind, seed=0):
+    lib = _lib.load()
+    h = tb.scoring.util_handle(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(seed + M + N + K)
+    A = torch.randn(M, K, device=DEV, generator=gen).half()
+    W = (torch.randn(N, taps * K, device=DEV, generator=gen) / math.sqrt(K * taps)).half()
+    bias = torch.randn(N, device=DEV, generator=gen) if use_bias else None
+    res16 = torch.randn(M, N, device=DEV, generator=gen).half() if res_kind == 16 else None
+    res32 = torch.randn(M, N, device=DEV, generator=gen) if res_kind == 32 else None
+    C16 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16) if out_kind in (16, 48) else None
+    C32 = torch.full((M, N), float("nan"), device=DEV) if out_kind in (32, 48) else None
+    rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, W.data_ptr(), M, N, K, taps, dil, T, _lib.ptr(bias), _lib.ptr(res16),
+                               _lib.ptr(res32), _lib.ptr(C16), _lib.ptr(C32), act, torch.cuda.current_stream().cuda_stream)
+    _lib.check(h, rc, "tag_debug_gemm_tc")
+    torch.cuda.synchronize()
+    res = res16.float() if res16 is not None else res32
+    ref = _gemm_ref(A.float(), W.float(), taps, dil, T, bias, res, act)
+    return C16, C32, ref
+
+
+CASES = [
+    # M, N, K, taps, dil, T, act, bias, res, out
+    (128, 256, 64, 1, 1, 1, 0, False, 0, 32),          # one tile, one k-block
+    (128, 256, 256, 1, 1, 1, 0, False, 0, 32),         # 4 k-blocks (ring wrap at 4 stages)
+    (300, 256, 1024, 1, 1, 1, 0, True, 32, 32),        # ragged M, 16 k-blocks, bias + fp32 residual (FFN2 / out-proj form)
+    (330, 768, 256, 1, 1, 1, 0, True, 0, 16),          # 3 n-tiles (QKV form)
+    (330, 1024, 256, 1, 1, 1, 2, True, 0, 16),         # FFN1 form, ReLU
+    (128 * 151, 256, 256, 1, 1, 1, 0, False, 0, 16),   # more tiles than SMs: persistent loop + both TMEM buffers
+    (256, 256, 256, 5, 1, 32, 1, False, 0, 16),        # conv1 form: 5 taps, GELU
+    (256, 256, 256, 5, 2, 32, 1, False, 16, 16),       # conv2 form: residual + GELU
+    (256, 256, 256, 5, 8, 32, 1, False, 16, 16),       # dilation 8: taps +-16 frames fall outside half the window
+    (384, 256, 256, 5, 4, 64, 1, False, 16, 16),       # T = 64 (2 windows / tile)
+    (96, 256, 256, 5, 4, 16, 1, False, 0, 16),         # T = 16, window count not filling the tile
+    (512, 256, 256, 5, 8, 256, 1, False, 16, 16),      # T = 256 (2 tiles / window)
+    (128 * 37, 256, 256, 5, 2, 32, 0, False, 0, 48),   # many conv tiles, both outputs
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"M{c[0]}_N{c[1]}_K{c[2]}_t{c[3]}d{c[4]}T{c[5]}" for c in CASES])
+def test_gemm_tc(case):
+    M, N, K, taps, dil, T, act, use_bias, res_kind, out_kind = case
+    C16, C32, ref = _run_tc(*case)
+    scale = max(1.0, ref.abs().max().item())
+    if C32 is not None:
+        err = (C32.double() - ref).abs().max().item()
+        assert err < 2e-4 * scale, _diag(C32, ref, "C32")
+    if C16 is not None:
+        err = (C16.double() - ref).abs().max().item()
+        assert err < 2e-3 * scale, _diag(C16, ref, "C16")
+
+
+def test_gemm_tc_rejects_unsupported_shapes():
+    lib = _lib.load()
+    h = tb.scoring.util_handle(DEV)
+    A = torch.zeros(96, 256, device=DEV, dtype=torch.float16)
+    W = torch.zeros(256, 1280, device=DEV, dtype=torch.float16)
+    Cc = torch.zeros(96, 256, device=DEV, dtype=torch.float16)
+    s = torch.cuda.current_stream().cuda_stream
+    # T = 48 neither divides 128 nor is a multiple of it
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 5, 1, 48, None, None, None, Cc.data_ptr(), None, 0, s) != 0
+    assert b"T dividing 128" in lib.tag_last_error(h)
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 100, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 0, s) != 0
+
+
+@pytest.mark.parametrize("tag", ["m5_t32", "m7_t256"])
+def test_encoder_tc_matches_reference_within_north_star_tolerance(tag):
+    g = golden_case(tag)
+    model = _model(g, "fp16_tc", max_windows=16)
+    # north-star: per-video scores and centroids within 1e-3 relative of the reference's fp32 path
+    _check_scores(g, model, tol_embed=2e-3, tol_score=1e-3)
+
+
+def test_encoder_tc_vs_fp32_mode_full_batch():
+    """Larger batch than the goldens (BASELINE config-1 size: 64 windows x 32 frames): tensor-core mode vs
+    the fp32 mode of the same library on the same inputs."""
+    g = golden_case("m5_t32")
+    vb = tb.make_videos(64, 32, seed=1337 + 1)
+    stats = g.stats()
+    res = {}
+    for prec in ("fp32", "fp16_tc"):
+        model = _model(g, prec, max_windows=64)
+        scorer = tb.TagScorer(model, stats, 32, 8, DEV)
+        enc = scorer.encode(scorer.to_device(vb), want_frames=True)
+        res[prec] = (enc["seq"].cpu(), enc["tc_window"].cpu(), enc["frames"].cpu())
+    e_seq = max_abs(res["fp32"][0], res["fp16_tc"][0])
+    e_tc = float(((res["fp32"][1] - res["fp16_tc"][1]).abs() / res["fp32"][1]).max())
+    print(f"tc-vs-fp32: seq {e_seq:.2e} tc rel {e_tc:.2e}")
+    assert e_seq < 2e-3 and e_tc < 1e-3
+
+
+def test_fused_pipeline_tc_scores():
+    g = golden_case("m5_t32")
+    model = _model(g, "fp16_tc", max_windows=16)
+    scorer = tb.TagScorer(model, g.stats(), clip_len=g.clip_len, stride=g.stride, device=DEV)
+    cen = torch.from_numpy(g.npz["centroids"]).to(DEV)
+    ac, tc = scorer.score_host(g.gen.pin(), cen)
+    d = scorer.scores_dict(g.gen, ac, tc)
+    e_ac = max(abs(d[k]["ac"] - v) / v for k, v in g.meta["ac"].items())
+    e_tc = max(abs(d[k]["tc"] - v) / v for k, v in g.meta["tc"].items())
+    print(f"fused tc pipeline: AC rel {e_ac:.2e} TC rel {e_tc:.2e}")
+    assert e_ac < 1e-3 and e_tc < 1e-3
+    assert int(scorer.last_flags.item()) == 0

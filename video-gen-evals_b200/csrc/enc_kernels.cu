@@ -1,0 +1,313 @@
+// Non-GEMM encoder kernels (norms, modality fusion, attention, output head). Templated on the
+// activation storage type: float (reference-precision mode) or __half (tensor-core mode); all
+// arithmetic is fp32. One warp owns one 256-wide row (8 channels per lane, 16/32-byte accesses).
+//
+// Replaces (reference model.py): GroupNorm(1,256) :32/:40; F.layer_norm no-affine :175; MinimalPerFrameFusion
+// :79-98 (kv-LN, constant-query logits, temperature/bias, softmax over modalities, weighted sum);
+// cls/positional embedding :187-188; nn.TransformerEncoderLayer self-attention + LayerNorms :145-146;
+// output normalisation :190-192 and eval.py:218-224 per-window temporal coherence.
+#include "common.cuh"
+#include "kernels.h"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int kD = TAG_D_MODEL;
+constexpr float kLnEps = 1e-5f;
+
+// ---------------------------------------------------------------- GroupNorm(1 group) over (T x 256) per window
+template <typename TA>
+__global__ void __launch_bounds__(256) k_groupnorm(const TA* __restrict__ z, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, TA* __restrict__ out, int T) {
+  __shared__ float red[33];
+  const int64_t w = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const TA* zw = z + w * (int64_t)T * kD;
+  TA* ow = out + w * (int64_t)T * kD;
+  float s = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    float v[8];
+    Row8<TA>::load(zw + (int64_t)t * kD + lane * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  const float n = (float)T * (float)kD;
+  const float mean = block_sum(s, red) / n;
+  float q = 0.f;
+  for (int t = warp; t < T; t += 8) {
+    float v[8];
+    Row8<TA>::load(zw + (int64_t)t * kD + lane * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q += d * d; }
+  }
+  const float var = block_sum(q, red) / n;          // biased, as torch group_norm
+  const float rstd = 1.0f / sqrtf(var + kLnEps);
+  float g[8], b[8];
+  Row8<float>::load(gamma + lane * 8, g);
+  Row8<float>::load(beta + lane * 8, b);
+  for (int t = warp; t < T; t += 8) {
+    float v[8];
+    Row8<TA>::load(zw + (int64_t)t * kD + lane * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
+    Row8<TA>::store(ow + (int64_t)t * kD + lane * 8, v);
+  }
+}
+
+// row LayerNorm statistics across a warp (two-pass)
+__device__ __forceinline__ void row_norm(float (&v)[8]) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += v[k];
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { v[k] -= mean; q += v[k] * v[k]; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / kD) + kLnEps);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] *= rstd;
+}
+
+// ---------------------------------------------------------------- A11 + A12 (front half)
+template <typename TA>
+__global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= p.R) return;
+  float g[8], b[8], qk[8];
+  Row8<float>::load(p.kv_gamma + lane * 8, g);
+  Row8<float>::load(p.kv_beta + lane * 8, b);
+  Row8<float>::load(p.qk + lane * 8, qk);
+  float kv[TAG_MAX_MODALITIES][8];
+  float logit[TAG_MAX_MODALITIES];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int m = 0; m < TAG_MAX_MODALITIES; ++m) {
+    if (m < p.M) {
+      float v[8];
+      Row8<TA>::load(reinterpret_cast<const TA*>(p.ps[m]) + r * kD + lane * 8, v);
+      if (p.pm[m] != nullptr) {
+        float u[8];
+        Row8<TA>::load(reinterpret_cast<const TA*>(p.pm[m]) + r * kD + lane * 8, u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += u[k];             // s = state + motion  (model.py:174)
+      }
+      row_norm(v);                                            // F.layer_norm, no affine (model.py:175)
+      row_norm(v);                                            // fusion.kv_ln (model.py:81) ...
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { v[k] = v[k] * g[k] + b[k]; kv[m][k] = v[k]; d += v[k] * qk[k]; }
+      d = warp_sum(d);                                        // Q . (Wk kv) / sqrt(D)
+      logit[m] = d * p.inv_tau[m] + p.lbias[m];               // model.py:89-91
+      mx = fmaxf(mx, logit[m]);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int m = 0; m < TAG_MAX_MODALITIES; ++m)
+    if (m < p.M) { logit[m] = expf(logit[m] - mx); den += logit[m]; }
+  float mix[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mix[k] = 0.f;
+#pragma unroll
+  for (int m = 0; m < TAG_MAX_MODALITIES; ++m)
+    if (m < p.M) {
+      const float a = logit[m] / den;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mix[k] += a * kv[m][k];
+      if (p.attn != nullptr && lane == 0) p.attn[r * p.M + m] = a;
+    }
+  Row8<TA>::store(reinterpret_cast<TA*>(p.mix) + r * kD + lane * 8, mix);
+}
+
+// ---------------------------------------------------------------- tokens = [cls ; frames] + PE
+template <typename TA>
+__global__ void __launch_bounds__(256) k_build_tokens(const TA* __restrict__ fused, const float* __restrict__ cls,
+                                                      const float* __restrict__ pe, float* __restrict__ x32,
+                                                      TA* __restrict__ x16, int64_t rows, int T) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int S = T + 1;
+  const int64_t n = r / S;
+  const int s = (int)(r - n * S);
+  float v[8], e[8];
+  if (s == 0) Row8<float>::load(cls + lane * 8, v);
+  else Row8<TA>::load(fused + (n * T + (s - 1)) * kD + lane * 8, v);
+  Row8<float>::load(pe + (int64_t)s * kD + lane * 8, e);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] += e[k];
+  Row8<float>::store(x32 + r * kD + lane * 8, v);
+  if (x16 != nullptr) Row8<TA>::store(x16 + r * kD + lane * 8, v);
+}
+
+// ---------------------------------------------------------------- self-attention, head_dim 32
+// one CTA per (window, head); K/V of the window-head staged in shared memory, one query per thread,
+// online softmax in registers.
+template <typename TA>
+__global__ void k_attention(const TA* __restrict__ qkv, TA* __restrict__ out, int S, int n_heads) {
+  extern __shared__ float sm[];
+  float* sK = sm;                 // [S][32]
+  float* sV = sm + (size_t)S * 32;
+  const int64_t n = blockIdx.x / n_heads;
+  const int h = blockIdx.x % n_heads;
+  const TA* base = qkv + n * (int64_t)S * (3 * kD);
+  for (int i = threadIdx.x; i < S * 32; i += blockDim.x) {
+    const int j = i >> 5, d = i & 31;
+    sK[i] = ldf<TA>(base + (int64_t)j * (3 * kD) + kD + h * 32 + d);
+    sV[i] = ldf<TA>(base + (int64_t)j * (3 * kD) + 2 * kD + h * 32 + d);
+  }
+  __syncthreads();
+  const float scale = 0.17677669529663688110f;      // 1/sqrt(32)
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    float q[32], acc[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { q[d] = ldf<TA>(base + (int64_t)i * (3 * kD) + h * 32 + d) * scale; acc[d] = 0.f; }
+    float m = -CUDART_INF_F, l = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float sc = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) sc = fmaf(q[d], sK[j * 32 + d], sc);
+      const float mn = fmaxf(m, sc);
+      const float corr = expf(m - mn);
+      const float pj = expf(sc - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) acc[d] = fmaf(pj, sV[j * 32 + d], acc[d] * corr);
+      m = mn;
+    }
+    const float inv = 1.0f / l;
+    TA* o = out + (n * S + i) * kD + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) stf<TA>(o + d, acc[d] * inv);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm with affine
+template <typename TA>
+__global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float* __restrict__ y32,
+                                                   TA* __restrict__ y16, int64_t rows) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float v[8], g[8], b[8];
+  Row8<float>::load(x + r * kD + lane * 8, v);
+  Row8<float>::load(gamma + lane * 8, g);
+  Row8<float>::load(beta + lane * 8, b);
+  row_norm(v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = v[k] * g[k] + b[k];
+  Row8<float>::store(y32 + r * kD + lane * 8, v);
+  if (y16 != nullptr) Row8<TA>::store(y16 + r * kD + lane * 8, v);
+}
+
+// ---------------------------------------------------------------- output head: one warp per window
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ tokens, int64_t n_windows, int S,
+                                                  float* __restrict__ seq, float* __restrict__ frame_embeds,
+                                                  float* __restrict__ tokens_out, float* __restrict__ tc_window) {
+  const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= n_windows) return;
+  float prev[8];
+  float tsum = 0.f;
+  for (int s = 0; s < S; ++s) {
+    float v[8];
+    const int64_t r = n * S + s;
+    Row8<float>::load(tokens + r * kD + lane * 8, v);
+    if (tokens_out != nullptr) Row8<float>::store(tokens_out + r * kD + lane * 8, v);
+    if (NORMALIZE) {
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ss += v[k] * v[k];
+      const float dn = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);      // F.normalize (model.py:191-192)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] / dn;
+    }
+    if (frame_embeds != nullptr) Row8<float>::store(frame_embeds + r * kD + lane * 8, v);
+    if (s == 0 && seq != nullptr) Row8<float>::store(seq + n * kD + lane * 8, v);
+    if (s >= 2) {                                             // eval.py:218-224: frames only (drop CLS)
+      float d2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[k] - prev[k]; d2 += d * d; }
+      tsum += sqrtf(warp_sum(d2));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) prev[k] = v[k];
+  }
+  if (tc_window != nullptr && lane == 0) tc_window[n] = (S >= 3) ? tsum / (float)(S - 2) : CUDART_NAN_F;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- launchers
+template <typename TA>
+cudaError_t launch_groupnorm(const TA* z, const float* gamma, const float* beta, TA* out, int64_t n_windows, int T,
+                             cudaStream_t s) {
+  if (n_windows <= 0) return cudaSuccess;
+  k_groupnorm<TA><<<(unsigned)n_windows, 256, 0, s>>>(z, gamma, beta, out, T);
+  return cudaGetLastError();
+}
+template cudaError_t launch_groupnorm<float>(const float*, const float*, const float*, float*, int64_t, int, cudaStream_t);
+template cudaError_t launch_groupnorm<__half>(const __half*, const float*, const float*, __half*, int64_t, int, cudaStream_t);
+
+template <typename TA>
+cudaError_t launch_merge_fusion(const MergeParams& p, cudaStream_t s) {
+  if (p.R <= 0) return cudaSuccess;
+  k_merge_fusion<TA><<<(unsigned)((p.R + 7) / 8), 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+template cudaError_t launch_merge_fusion<float>(const MergeParams&, cudaStream_t);
+template cudaError_t launch_merge_fusion<__half>(const MergeParams&, cudaStream_t);
+
+template <typename TA>
+cudaError_t launch_build_tokens(const TA* fused, const float* cls, const float* pe, float* x32, TA* x16,
+                                int64_t n_windows, int T, cudaStream_t s) {
+  const int64_t rows = n_windows * (T + 1);
+  if (rows <= 0) return cudaSuccess;
+  k_build_tokens<TA><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(fused, cls, pe, x32, x16, rows, T);
+  return cudaGetLastError();
+}
+template cudaError_t launch_build_tokens<float>(const float*, const float*, const float*, float*, float*, int64_t, int, cudaStream_t);
+template cudaError_t launch_build_tokens<__half>(const __half*, const float*, const float*, float*, __half*, int64_t, int, cudaStream_t);
+
+template <typename TA>
+cudaError_t launch_attention(const TA* qkv, TA* out, int64_t n_windows, int S, int n_heads, cudaStream_t s) {
+  if (n_windows <= 0) return cudaSuccess;
+  const size_t smem = (size_t)S * 32 * 2 * sizeof(float);
+  int threads = ((S + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_attention<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_attention<TA><<<(unsigned)(n_windows * n_heads), threads, smem, s>>>(qkv, out, S, n_heads);
+  return cudaGetLastError();
+}
+template cudaError_t launch_attention<float>(const float*, float*, int64_t, int, int, cudaStream_t);
+template cudaError_t launch_attention<__half>(const __half*, __half*, int64_t, int, int, cudaStream_t);
+
+template <typename TA>
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* y32, TA* y16, int64_t rows,
+                             cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  k_layernorm<TA><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, gamma, beta, y32, y16, rows);
+  return cudaGetLastError();
+}
+template cudaError_t launch_layernorm<float>(const float*, const float*, const float*, float*, float*, int64_t, cudaStream_t);
+template cudaError_t launch_layernorm<__half>(const float*, const float*, const float*, float*, __half*, int64_t, cudaStream_t);
+
+cudaError_t launch_finalize(const float* tokens, int64_t n_windows, int S, float* seq, float* frame_embeds,
+                            float* tokens_out, float* tc_window, cudaStream_t s) {
+  if (n_windows <= 0) return cudaSuccess;
+  k_finalize<true><<<(unsigned)((n_windows + 7) / 8), 256, 0, s>>>(tokens, n_windows, S, seq, frame_embeds, tokens_out, tc_window);
+  return cudaGetLastError();
+}
+
+// eval.py:218-224 on already-normalised frame embeddings [N, S, 256] (S = T+1, row 0 = CLS)
+cudaError_t launch_window_tc(const float* frame_embeds, int64_t n_windows, int S, float* tc_window, cudaStream_t s) {
+  if (n_windows <= 0) return cudaSuccess;
+  k_finalize<false><<<(unsigned)((n_windows + 7) / 8), 256, 0, s>>>(frame_embeds, n_windows, S, nullptr, nullptr, nullptr, tc_window);
+  return cudaGetLastError();
+}

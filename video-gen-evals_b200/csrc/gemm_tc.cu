@@ -1,0 +1,409 @@
+// Tensor-core GEMM for the encoder's dense layers on sm_100a: TMA -> shared memory (128B swizzle) ->
+// tcgen05.mma (fp16 operands, fp32 accumulators in TMEM) -> tcgen05.ld epilogue with fused
+// bias / residual / activation.
+//
+//   C[r, n] = act( sum_{j<taps} sum_{k<K} A[r + (j - taps/2)*dil, k] * W[n, j*K + k] + bias[n] + res[r, n] )
+//
+// Replaces the reference's nn.Conv1d(k=5, dilation d, zero padding 2d) / 1x1 conv / nn.Linear calls
+// (model.py:25-30, :46, :50, :84-97, :145). The dilated conv is NOT lowered through im2col: activations
+// are viewed as a 3-D tensor (channel, t, window) and the five taps are five TMA loads whose t
+// coordinate is shifted by (j-2)*dil — TMA's out-of-bounds zero fill IS the conv's zero padding — all
+// accumulating into one TMEM tile.
+//
+// CTA = 320 threads, persistent over 128x256 output tiles:
+//   warp 0      TMA producer (one elected lane), 4-stage ring of {A 128x64, B 256x64} fp16 tiles
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma 128x256x16 per stage
+//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns at a time; 2 TMEM accumulator buffers
+//               (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+// Descriptor encodings follow the PTX ISA tcgen05 matrix/instruction descriptor tables (cross-checked
+// against CUTLASS cute/arch/mma_sm100_desc.hpp).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;       // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+struct TcParams {
+  int64_t M;
+  int N;
+  int kb_per_tap;       // K / 64
+  int taps, dil;
+  int mode;             // 0 plain rows, 1 conv with T <= 128 (tile = 128/T windows), 2 conv with T % 128 == 0
+  int T, wpt, tpw;      // frames per window, windows per tile (mode 1), tiles per window (mode 2)
+  int64_t m_tiles;
+  int n_tiles;
+  const float* bias;
+  const __half* res16; int ldr;
+  const float* res32;
+  __half* C16; int ldc;
+  float* C32;
+  int act;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows 128 B apart, 8-row groups
+// 1024 B apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (this kernel runs one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int n_kb = p.taps * p.kb_per_tap;
+  const int64_t total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int64_t m_tile = tile / p.n_tiles;
+        const int n_tile = (int)(tile - m_tile * p.n_tiles);
+        int c1_base, c2;
+        if (p.mode == 0) { c1_base = (int)(m_tile * BLOCK_M); c2 = 0; }
+        else if (p.mode == 1) { c1_base = 0; c2 = (int)(m_tile * p.wpt); }
+        else { c2 = (int)(m_tile / p.tpw); c1_base = (int)(m_tile - (int64_t)c2 * p.tpw) * BLOCK_M; }
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const int j = kb / p.kb_per_tap;
+          const int kc = kb - j * p.kb_per_tap;
+          const int shift = (p.taps > 1) ? (j - p.taps / 2) * p.dil : 0;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+          tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      int stage = 0; uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);           // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);                  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                      // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));                          // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // which 128 accumulator columns
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int64_t m_tile = tile / p.n_tiles;
+      const int n_tile = (int)(tile - m_tile * p.n_tiles);
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t r = m_tile * BLOCK_M + q * 32 + lane;
+      const bool row_ok = r < p.M;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), raw);
+        if (row_ok) {
+          const int n = n_tile * BLOCK_N + col;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+          }
+          if (p.res16 != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(rp + i);
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
+            }
+          }
+          if (p.res32 != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(p.res32 + r * (int64_t)p.N + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 f = __ldg(rp + i);
+              v[i * 4] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.C16 != nullptr) {
+            uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+              op[i] = u;
+            }
+          }
+          if (p.C32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.C32 + r * (int64_t)p.N + n);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct TcContext {
+  EncodeTiledFn encode = nullptr;
+  int num_sms = 148;
+};
+
+TcContext* tc_context_create(int device, char* err, int errlen) {
+  TcContext* c = new TcContext();
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    snprintf(err, errlen, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    delete c;
+    return nullptr;
+  }
+  c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+  e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) {
+    snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void tc_context_destroy(TcContext* c) { delete c; }
+
+cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char* err, int errlen) {
+  if (g.M <= 0) return cudaSuccess;
+  auto bad = [&](const char* msg) {
+    snprintf(err, errlen, "gemm_tc: %s (M=%lld N=%d K=%d taps=%d T=%d lda=%d)", msg, (long long)g.M, g.N, g.K, g.taps, g.T, g.lda);
+    return cudaErrorInvalidValue;
+  };
+  if (ctx == nullptr) return bad("no tensor-core context");
+  if (g.N % BLOCK_N) return bad("N must be a multiple of 256");
+  if (g.K % BLOCK_K || g.K <= 0) return bad("K must be a positive multiple of 64");
+  if (g.lda % 8 || (reinterpret_cast<uintptr_t>(g.A) & 15)) return bad("A must be 16-byte aligned with lda % 8 == 0");
+  if (reinterpret_cast<uintptr_t>(g.W) & 15) return bad("W must be 16-byte aligned");
+  if (g.A2 != nullptr) return bad("second K segment not built yet");
+  if (g.C16 == nullptr && g.C32 == nullptr) return bad("no output");
+  if (g.C16 && ((g.ldc % 8) || (reinterpret_cast<uintptr_t>(g.C16) & 15))) return bad("C16 alignment");
+  if (g.res16 && ((g.ldr % 8) || (reinterpret_cast<uintptr_t>(g.res16) & 15))) return bad("res16 alignment");
+
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.kb_per_tap = g.K / BLOCK_K; p.taps = g.taps; p.dil = g.dil; p.T = g.T;
+  p.bias = g.bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
+  p.n_tiles = g.N / BLOCK_N;
+  p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
+
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  if (g.taps > 1) {
+    if (g.T < 1 || g.M % g.T) return bad("conv rows must be whole windows");
+    const int64_t W = g.M / g.T;
+    if (g.T <= BLOCK_M) {
+      if (BLOCK_M % g.T) return bad("tensor-core conv needs T dividing 128 or a multiple of 128");
+      p.mode = 1; p.wpt = BLOCK_M / g.T; p.tpw = 1;
+      box[0] = BLOCK_K; box[1] = (cuuint32_t)g.T; box[2] = (cuuint32_t)p.wpt;
+    } else {
+      if (g.T % BLOCK_M) return bad("tensor-core conv needs T dividing 128 or a multiple of 128");
+      p.mode = 2; p.wpt = 1; p.tpw = g.T / BLOCK_M;
+      box[0] = BLOCK_K; box[1] = BLOCK_M; box[2] = 1;
+    }
+    gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)g.T; gdim[2] = (cuuint64_t)W;
+    gstr[0] = (cuuint64_t)g.lda * 2; gstr[1] = (cuuint64_t)g.T * g.lda * 2;
+  } else {
+    p.mode = 0; p.wpt = 1; p.tpw = 1;
+    box[0] = BLOCK_K; box[1] = BLOCK_M; box[2] = 1;
+    gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)g.M; gdim[2] = 1;
+    gstr[0] = (cuuint64_t)g.lda * 2; gstr[1] = (cuuint64_t)g.M * g.lda * 2;
+  }
+  CUtensorMap map_a, map_b;
+  CUresult r = ctx->encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(g.A), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
+  const int64_t ktot = (int64_t)g.taps * g.K;
+  cuuint64_t bdim[2] = {(cuuint64_t)ktot, (cuuint64_t)g.N};
+  cuuint64_t bstr[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t bbox[2] = {BLOCK_K, BLOCK_N};
+  cuuint32_t bes[2] = {1, 1};
+  r = ctx->encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(g.W), bdim, bstr, bbox, bes,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(W) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
+
+  const int64_t total = p.m_tiles * p.n_tiles;
+  const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
+  k_gemm_tc<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  return cudaGetLastError();
+}

@@ -1,0 +1,109 @@
+// Internal launcher interface between tag_api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/tag_b200.h"
+
+// ------------------------------------------------------------------ K1 feature fuse
+struct FuseParams {
+  int M;
+  int kind[TAG_MAX_MODALITIES];
+  int raw_dim[TAG_MAX_MODALITIES], diff_dim[TAG_MAX_MODALITIES];
+  int raw_off[TAG_MAX_MODALITIES], diff_off[TAG_MAX_MODALITIES];       // fp32 feats columns
+  int raw_off16[TAG_MAX_MODALITIES], diff_off16[TAG_MAX_MODALITIES];   // padded fp16 operand columns
+  const float* src[TAG_MAX_MODALITIES];
+  const int64_t* frame_offset;
+  const float* mean;        // [D] or null
+  const float* stdv;        // [D] or null
+  const int32_t* win_video;
+  const int32_t* win_start;
+  int64_t n_windows;
+  int T, D, D16;
+  float* feats;             // [N,T,D] or null
+  __half* feats16;          // [N,T,D16] or null (pad columns must be pre-zeroed by the caller)
+  int32_t* flags;           // [1] or null
+};
+cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s);
+
+// ------------------------------------------------------------------ K3 / K4 / N1 / N2
+cudaError_t launch_centroid_accumulate(const float* z, const int32_t* labels, int64_t n, int C,
+                                       float* sums_counts, cudaStream_t s);
+cudaError_t launch_centroid_finalize(const float* sums_counts, int C, float* centroids, float* counts, cudaStream_t s);
+cudaError_t launch_score(const float* seq, const float* tcw, const int64_t* seg, const int32_t* label,
+                         const float* cen, int C, int64_t V, float* ac, float* tc, cudaStream_t s);
+cudaError_t launch_stats_accumulate(const float* x, int64_t rows, int D, double* sum, double* sumsq, cudaStream_t s);
+cudaError_t launch_tcl_forward(const float* z, const int32_t* y, int64_t B, float temperature, float k1, float k2,
+                               float* loss_rows, cudaStream_t s);
+
+// ------------------------------------------------------------------ encoder building blocks
+// Generic fp32 CUDA-core GEMM with conv taps:  C[M,N] = act( sum_j A[row+shift_j, :K] . W[n, j*K : (j+1)*K] + bias + res )
+struct GemmF32 {
+  const float* A; int lda;          // [M, K] rows (row stride lda)
+  const float* W; int ldw;          // [N, taps*K] (K contiguous per tap)
+  const float* bias;                // [N] or null
+  const float* res; int ldr;        // [M, N] or null
+  float* C; int ldc;
+  int M, N, K;
+  int taps, dil, T;                 // taps>1: rows are (window, t) with T frames; shift_j = (j - taps/2)*dil, zero outside the window
+  int act;                          // 0 none, 1 gelu(erf), 2 relu
+};
+cudaError_t launch_gemm_f32(const GemmF32& g, cudaStream_t s);
+
+template <typename TA>
+cudaError_t launch_groupnorm(const TA* z, const float* gamma, const float* beta, TA* out, int64_t n_windows, int T,
+                             cudaStream_t s);
+
+struct MergeParams {
+  int M;
+  const void* ps[TAG_MAX_MODALITIES];   // state proj outputs [R,256]
+  const void* pm[TAG_MAX_MODALITIES];   // motion proj outputs or null
+  float inv_tau[TAG_MAX_MODALITIES], lbias[TAG_MAX_MODALITIES];
+  const float* kv_gamma; const float* kv_beta;
+  const float* qk;                      // [256] = Wk^T (Wq LN_q(latent)) / sqrt(256)
+  void* mix;                            // [R,256]  sum_m A_m kv_m
+  float* attn;                          // [R,M] or null
+  int64_t R;
+};
+template <typename TA> cudaError_t launch_merge_fusion(const MergeParams& p, cudaStream_t s);
+
+// tokens[n,0] = cls + pe[0]; tokens[n,t+1] = fused[n,t] + pe[t+1]   (model.py:187-188)
+template <typename TA>
+cudaError_t launch_build_tokens(const TA* fused, const float* cls, const float* pe, float* x32, TA* x16_or_null,
+                                int64_t n_windows, int T, cudaStream_t s);
+
+// softmax(QK^T/sqrt(32)) V per (window, head); qkv [N*S, 768] -> out [N*S, 256]
+template <typename TA>
+cudaError_t launch_attention(const TA* qkv, TA* out, int64_t n_windows, int S, int n_heads, cudaStream_t s);
+
+// y = LayerNorm(x) * gamma + beta over 256 columns (x fp32 pre-norm sum), writes fp32 and optionally TA copy
+template <typename TA>
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* y32, TA* y16_or_null,
+                             int64_t rows, cudaStream_t s);
+
+// model.py:190-192 + eval.py:218-224: normalise tokens, seq embed, per-window TC
+cudaError_t launch_finalize(const float* tokens, int64_t n_windows, int S, float* seq, float* frame_embeds,
+                            float* tokens_out, float* tc_window, cudaStream_t s);
+
+cudaError_t launch_window_tc(const float* frame_embeds, int64_t n_windows, int S, float* tc_window, cudaStream_t s);
+
+// ------------------------------------------------------------------ tensor-core (tcgen05) GEMM
+struct GemmTC {
+  const __half* A;      // activations, [M, lda] (K contiguous)
+  int64_t M; int lda;
+  const __half* A2;     // optional second K-segment source (same shape conventions), null if unused
+  int lda2; int K2;
+  const __half* W;      // [N, Ktot] K-major, Ktot = taps*K + K2
+  int N, K;
+  int taps, dil, T;     // conv: rows are (window, t)
+  const float* bias;    // [N] or null
+  const __half* res16; int ldr;   // residual (fp16) or null
+  const float* res32;             // residual (fp32) or null (ld = N)
+  __half* C16; int ldc;           // fp16 output or null
+  float* C32;                     // fp32 output or null (ld = N)
+  int act;
+};
+struct TcContext;   // opaque: driver entry points + cached tensor maps
+TcContext* tc_context_create(int device, char* err, int errlen);
+void tc_context_destroy(TcContext*);
+cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char* err, int errlen);

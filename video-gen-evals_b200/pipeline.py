@@ -1,0 +1,143 @@
+"""The fused, device-resident TAG scoring pipeline: what `python eval.py` (reference eval.py:350-466)
+does between "arrays loaded" and "video_scores.json", as three native calls per batch of videos:
+
+    tag_encode_windows   K1 feature fuse + K2 encoder (+ fused per-window TC), chunked in HBM
+    tag_centroid_*       K3 per-action centroid sums -> [allreduce across ranks] -> normalise
+    tag_score            K4 per-video AC (distance to centroid) and TC (mean of window TCs)
+
+Multi-GPU: videos are block-sharded across ranks (`shard_range`), every rank scores
+its own block with no data-path communication; the only collective is the all-reduce of the packed
+[C,257] centroid sums/counts buffer during the centroid build.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .features import DeviceVideos, stats_vectors
+from .model import HumanActionScorer
+from .scoring import allreduce_centroid_sums, centroid_accumulate, centroid_finalize, util_handle
+from .synth import VideoBatch
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of `n` videos owned by `rank` (keeps a video's windows on one rank)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def window_table(lengths: Sequence[int], clip_len: int, stride: int):
+    """(win_video int32[N], win_start int32[N], seg_offsets int64[V+1]) for `sample_all_windows_npz`
+    (reference utils.py:888-911), vectorised."""
+    L = np.asarray(lengths, dtype=np.int64)
+    stride = max(1, int(stride))
+    nwin = np.where(L < clip_len, 1, (L - clip_len) // stride + 1)
+    seg = np.zeros(len(L) + 1, dtype=np.int64)
+    np.cumsum(nwin, out=seg[1:])
+    win_video = np.repeat(np.arange(len(L), dtype=np.int32), nwin)
+    win_start = (np.arange(seg[-1], dtype=np.int64) - seg[:-1][win_video]) * stride
+    return win_video.astype(np.int32), win_start.astype(np.int32), seg
+
+
+class TagScorer:
+    def __init__(self, model: HumanActionScorer, stats, clip_len: int = 32, stride: int = 8, device=None):
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise _lib.TagError("TagScorer needs a CUDA (sm_100a) device; there is no CPU path")
+        self.clip_len, self.stride = int(clip_len), int(stride)
+        self.mean, self.std = stats_vectors(stats, model.modalities, self.device)
+        self.model.eval()
+        self._tables: Dict[tuple, tuple] = {}
+
+    # ------------------------------------------------------------------
+    def to_device(self, vb: VideoBatch) -> DeviceVideos:
+        return DeviceVideos(vb, self.model.modalities, self.device)
+
+    def _table(self, dv: DeviceVideos):
+        key = (id(dv), self.clip_len, self.stride)
+        if key not in self._tables:
+            wv, ws, seg = window_table(dv.lengths, self.clip_len, self.stride)
+            self._tables = {key: (torch.from_numpy(wv).to(self.device), torch.from_numpy(ws).to(self.device),
+                                  torch.from_numpy(seg).to(self.device), int(seg[-1]))}
+        return self._tables[key]
+
+    def encode(self, dv: DeviceVideos, want_frames: bool = False):
+        """-> dict(seq [N,256], tc_window [N], seg [V+1], frames [N,T+1,256]|None, flags int32[1])"""
+        lib = _lib.load()
+        wv, ws, seg, N = self._table(dv)
+        T = self.clip_len
+        h = self.model.handle(self.device, T)
+        seq = torch.empty(N, 256, device=self.device, dtype=torch.float32)
+        tcw = torch.empty(N, device=self.device, dtype=torch.float32)
+        frames = torch.empty(N, T + 1, 256, device=self.device, dtype=torch.float32) if want_frames else None
+        flags = torch.zeros(1, device=self.device, dtype=torch.int32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(h, lib.tag_encode_windows(h, C.byref(dv.c), _lib.ptr(self.mean), _lib.ptr(self.std), wv.data_ptr(),
+                                                 ws.data_ptr(), N, T, seq.data_ptr(), _lib.ptr(frames), None, tcw.data_ptr(),
+                                                 flags.data_ptr(), stream), "tag_encode_windows")
+        return {"seq": seq, "tc_window": tcw, "seg": seg, "frames": frames, "flags": flags, "win_video": wv}
+
+    # ------------------------------------------------------------------ centroid build (config 3)
+    def centroid_sums(self, dv: DeviceVideos, n_classes: int) -> torch.Tensor:
+        """Local [C,257] sums||counts of this rank's videos (window label = its video's class)."""
+        enc = self.encode(dv)
+        vid_label = torch.tensor(dv.vb.cls_idx, device=self.device, dtype=torch.int32)
+        y = vid_label.index_select(0, enc["win_video"].long()).contiguous()
+        sc = torch.zeros(n_classes, 257, device=self.device, dtype=torch.float32)
+        centroid_accumulate(enc["seq"], y, sc)
+        return sc
+
+    def build_centroids(self, dv: DeviceVideos, n_classes: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """build_real_centroids (eval.py:260-286) over this rank's shard + the one all-reduce."""
+        sc = self.centroid_sums(dv, n_classes)
+        allreduce_centroid_sums(sc, group)
+        return centroid_finalize(sc)
+
+    # ------------------------------------------------------------------ scoring (config 2)
+    def score(self, dv: DeviceVideos, centroids: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        """-> (ac [V], tc [V]) device tensors; ac is NaN for videos whose class has no centroid."""
+        lib = _lib.load()
+        enc = self.encode(dv)
+        V = dv.n_videos
+        if labels is None:
+            labels = torch.tensor(dv.vb.cls_idx, device=self.device, dtype=torch.int32)
+        ac = torch.empty(V, device=self.device, dtype=torch.float32)
+        tc = torch.empty(V, device=self.device, dtype=torch.float32)
+        h = util_handle(self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(h, lib.tag_score(h, enc["seq"].data_ptr(), enc["tc_window"].data_ptr(), enc["seg"].data_ptr(),
+                                        labels.data_ptr(), centroids.data_ptr(), int(centroids.shape[0]), V, ac.data_ptr(),
+                                        tc.data_ptr(), stream), "tag_score")
+        self.last_flags = enc["flags"]
+        return ac, tc
+
+    def score_host(self, vb_host: VideoBatch, centroids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End-to-end call with HOST buffers: H2D of every input array, score, D2H of the per-video
+        results. This is the `e2e` leg of bench.py. Returns CPU tensors (ac [V], tc [V])."""
+        dv = self.to_device(vb_host)
+        ac, tc = self.score(dv, centroids)
+        out = torch.stack([ac, tc], 0).cpu()
+        self._tables = {}
+        return out[0], out[1]
+
+    def scores_dict(self, vb: VideoBatch, ac: torch.Tensor, tc: torch.Tensor) -> Dict[str, Dict[str, float]]:
+        """{video_id: {"ac","tc"}} as eval.py:439-447 (a key is absent when the reference would skip it)."""
+        ac, tc = ac.cpu().tolist(), tc.cpu().tolist()
+        out = {}
+        for v, name in enumerate(vb.names):
+            e = {}
+            if ac[v] == ac[v]:
+                e["ac"] = float(ac[v])
+            if tc[v] == tc[v]:
+                e["tc"] = float(tc[v])
+            out[os.path.splitext(name)[0]] = e
+        return out
