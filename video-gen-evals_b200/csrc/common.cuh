@@ -41,6 +41,23 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// Branch-free GELU for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, below
+// fp32 round-off of the surrounding math and far below the fp16 rounding of the stored activation) with
+// MUFU rcp/ex2 — ~16 instructions per element instead of erff's ~30, which is what lets the epilogue warps keep
+// pace with the MMA pipe (budget: 40 thread-instructions per output element at K = 1280).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);            // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 // activation storage type helpers: the encoder keeps activations as float (fp32 mode) or
 // __half (tensor-core mode); all arithmetic is fp32.
 template <typename T> __device__ __forceinline__ float ldf(const T* p);

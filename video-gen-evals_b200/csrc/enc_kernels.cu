@@ -142,44 +142,89 @@ __global__ void __launch_bounds__(256) k_build_tokens(const TA* __restrict__ fus
 }
 
 // ---------------------------------------------------------------- self-attention, head_dim 32
-// one CTA per (window, head); K/V of the window-head staged in shared memory, one query per thread,
-// online softmax in registers.
-template <typename TA>
-__global__ void k_attention(const TA* __restrict__ qkv, TA* __restrict__ out, int S, int n_heads) {
-  extern __shared__ float sm[];
-  float* sK = sm;                 // [S][32]
-  float* sV = sm + (size_t)S * 32;
-  const int64_t n = blockIdx.x / n_heads;
-  const int h = blockIdx.x % n_heads;
+// One CTA per (window, group of HPC heads); one thread per (head, query). K/V of the group are staged in shared
+// memory as fp32 [S][HPC][36] (the 4-float pad keeps two heads read by one warp on different banks); every thread
+// walks the keys with 128-bit shared loads (a warp reads one address -> broadcast) and an online softmax in the
+// exp2 domain. For S = 33 and 8 heads, 264 of 288 threads are busy (one query per lane would leave 31/64 idle).
+constexpr int kHeadPad = 36;
+
+template <typename TA> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) { Row8<float>::load(p, v); }
+};
+template <> struct Vec8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) { Row8<__half>::load(p, v); }
+};
+
+template <typename TA, int HPC>
+__global__ void __launch_bounds__(640) k_attention(const TA* __restrict__ qkv, TA* __restrict__ out, int S, int n_heads) {
+  extern __shared__ __align__(16) float sm[];
+  const int rowf = HPC * kHeadPad;
+  float* sK = sm;                               // [S][HPC][36]
+  float* sV = sm + (size_t)S * rowf;
+  const int groups = n_heads / HPC;
+  const int64_t n = blockIdx.x / groups;
+  const int h0 = (blockIdx.x % groups) * HPC;
   const TA* base = qkv + n * (int64_t)S * (3 * kD);
-  for (int i = threadIdx.x; i < S * 32; i += blockDim.x) {
-    const int j = i >> 5, d = i & 31;
-    sK[i] = ldf<TA>(base + (int64_t)j * (3 * kD) + kD + h * 32 + d);
-    sV[i] = ldf<TA>(base + (int64_t)j * (3 * kD) + 2 * kD + h * 32 + d);
+  // stage K and V: units of 8 elements
+  for (int u = threadIdx.x; u < S * HPC * 4; u += blockDim.x) {
+    const int j = u / (HPC * 4), c = u - j * (HPC * 4);
+    const int h = c >> 2, part = c & 3;
+    float k8[8], v8[8];
+    Vec8<TA>::load(base + (int64_t)j * (3 * kD) + kD + (h0 + h) * 32 + part * 8, k8);
+    Vec8<TA>::load(base + (int64_t)j * (3 * kD) + 2 * kD + (h0 + h) * 32 + part * 8, v8);
+    float* kd = sK + j * rowf + h * kHeadPad + part * 8;
+    float* vd = sV + j * rowf + h * kHeadPad + part * 8;
+    *reinterpret_cast<float4*>(kd) = make_float4(k8[0], k8[1], k8[2], k8[3]);
+    *reinterpret_cast<float4*>(kd + 4) = make_float4(k8[4], k8[5], k8[6], k8[7]);
+    *reinterpret_cast<float4*>(vd) = make_float4(v8[0], v8[1], v8[2], v8[3]);
+    *reinterpret_cast<float4*>(vd + 4) = make_float4(v8[4], v8[5], v8[6], v8[7]);
   }
   __syncthreads();
-  const float scale = 0.17677669529663688110f;      // 1/sqrt(32)
-  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+  const float scale = 0.17677669529663688110f * 1.4426950408889634f;      // log2(e) / sqrt(32)
+  for (int idx = threadIdx.x; idx < HPC * S; idx += blockDim.x) {
+    const int h = idx / S, i = idx - h * S;
     float q[32], acc[32];
+    const TA* qp = base + (int64_t)i * (3 * kD) + (h0 + h) * 32;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) { q[d] = ldf<TA>(base + (int64_t)i * (3 * kD) + h * 32 + d) * scale; acc[d] = 0.f; }
+    for (int c = 0; c < 4; ++c) {
+      float t8[8];
+      Vec8<TA>::load(qp + c * 8, t8);
+#pragma unroll
+      for (int d = 0; d < 8; ++d) { q[c * 8 + d] = t8[d] * scale; acc[c * 8 + d] = 0.f; }
+    }
     float m = -CUDART_INF_F, l = 0.f;
-    for (int j = 0; j < S; ++j) {
+    const float* kp = sK + h * kHeadPad;
+    const float* vp = sV + h * kHeadPad;
+    for (int j = 0; j < S; ++j, kp += rowf, vp += rowf) {
       float sc = 0.f;
 #pragma unroll
-      for (int d = 0; d < 32; ++d) sc = fmaf(q[d], sK[j * 32 + d], sc);
+      for (int c = 0; c < 8; ++c) {
+        const float4 k4 = *reinterpret_cast<const float4*>(kp + c * 4);
+        sc = fmaf(q[c * 4], k4.x, sc); sc = fmaf(q[c * 4 + 1], k4.y, sc);
+        sc = fmaf(q[c * 4 + 2], k4.z, sc); sc = fmaf(q[c * 4 + 3], k4.w, sc);
+      }
       const float mn = fmaxf(m, sc);
-      const float corr = expf(m - mn);
-      const float pj = expf(sc - mn);
-      l = l * corr + pj;
+      const float corr = exp2f(m - mn);
+      const float pj = exp2f(sc - mn);
+      l = fmaf(l, corr, pj);
 #pragma unroll
-      for (int d = 0; d < 32; ++d) acc[d] = fmaf(pj, sV[j * 32 + d], acc[d] * corr);
+      for (int c = 0; c < 8; ++c) {
+        const float4 v4 = *reinterpret_cast<const float4*>(vp + c * 4);
+        acc[c * 4] = fmaf(pj, v4.x, acc[c * 4] * corr); acc[c * 4 + 1] = fmaf(pj, v4.y, acc[c * 4 + 1] * corr);
+        acc[c * 4 + 2] = fmaf(pj, v4.z, acc[c * 4 + 2] * corr); acc[c * 4 + 3] = fmaf(pj, v4.w, acc[c * 4 + 3] * corr);
+      }
       m = mn;
     }
     const float inv = 1.0f / l;
-    TA* o = out + (n * S + i) * kD + h * 32;
+    TA* o = out + (n * S + i) * kD + (h0 + h) * 32;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) stf<TA>(o + d, acc[d] * inv);
+    for (int c = 0; c < 4; ++c) {
+      float t8[8];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) t8[d] = acc[c * 8 + d] * inv;
+      Row8<TA>::store(o + c * 8, t8);
+    }
   }
 }
 
@@ -272,18 +317,29 @@ cudaError_t launch_build_tokens(const TA* fused, const float* cls, const float* 
 template cudaError_t launch_build_tokens<float>(const float*, const float*, const float*, float*, float*, int64_t, int, cudaStream_t);
 template cudaError_t launch_build_tokens<__half>(const __half*, const float*, const float*, float*, __half*, int64_t, int, cudaStream_t);
 
+template <typename TA, int HPC>
+static cudaError_t launch_attention_hpc(const TA* qkv, TA* out, int64_t n_windows, int S, int n_heads, cudaStream_t s) {
+  const size_t smem = (size_t)2 * S * HPC * kHeadPad * sizeof(float);
+  int threads = ((HPC * S + 31) / 32) * 32;
+  if (threads > 640) threads = 640;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_attention<TA, HPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k_attention<TA, HPC><<<(unsigned)(n_windows * (n_heads / HPC)), threads, smem, s>>>(qkv, out, S, n_heads);
+  return cudaGetLastError();
+}
+
 template <typename TA>
 cudaError_t launch_attention(const TA* qkv, TA* out, int64_t n_windows, int S, int n_heads, cudaStream_t s) {
   if (n_windows <= 0) return cudaSuccess;
-  const size_t smem = (size_t)S * 32 * 2 * sizeof(float);
-  int threads = ((S + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_attention<TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  k_attention<TA><<<(unsigned)(n_windows * n_heads), threads, smem, s>>>(qkv, out, S, n_heads);
-  return cudaGetLastError();
+  // largest head group whose K/V fit comfortably in shared memory
+  auto fits = [&](int hpc) { return n_heads % hpc == 0 && (size_t)2 * S * hpc * kHeadPad * sizeof(float) <= 160 * 1024; };
+  if (fits(8)) return launch_attention_hpc<TA, 8>(qkv, out, n_windows, S, n_heads, s);
+  if (fits(4)) return launch_attention_hpc<TA, 4>(qkv, out, n_windows, S, n_heads, s);
+  if (fits(2)) return launch_attention_hpc<TA, 2>(qkv, out, n_windows, S, n_heads, s);
+  if (fits(1)) return launch_attention_hpc<TA, 1>(qkv, out, n_windows, S, n_heads, s);
+  return cudaErrorInvalidValue;       // S > ~560 tokens per window: not built
 }
 template cudaError_t launch_attention<float>(const float*, float*, int64_t, int, int, cudaStream_t);
 template cudaError_t launch_attention<__half>(const __half*, __half*, int64_t, int, int, cudaStream_t);

@@ -271,7 +271,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
           if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
           } else if (p.act == 2) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);

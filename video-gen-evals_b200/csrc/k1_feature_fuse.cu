@@ -12,9 +12,8 @@
 //   utils.py:472-514  z-score (x-mean)/(std+1e-6) and concat
 //
 // HBM-bound: per (window, frame) reads sum(raw_dims)*4 B and writes D*4 B (fp32 feats) and/or D16*2 B
-// (padded fp16 operand for the tensor-core encoder). One CTA per window walks its T frames; the
-// previous frame is re-read through L1/L2 (same CTA touched it one iteration earlier), so DRAM sees
-// each source frame once per window.
+// (padded fp16 operand for the tensor-core encoder). One warp per (window, frame), 8 consecutive frames per
+// CTA; the previous frame is re-read through L1/L2, so DRAM sees each source frame about once per window.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -39,81 +38,76 @@ struct Norm {
   }
 };
 
+// One warp per (window, frame): every reduction (cosine norms, keypoint centre / scale / 2x2 correlation) is a
+// warp shuffle, so there is no block barrier and no shared memory; the previous frame's quantities are recomputed
+// from its row (an L1/L2 hit: the neighbouring warp of the same CTA streams that row as its current frame), which
+// keeps all of a warp's ~11 KB of loads independent and in flight together.
 __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
-  __shared__ float red[33];
-  __shared__ float s_dn[TAG_MAX_MODALITIES];       // previous frame's cosine denominators
-  __shared__ float s_kp[2][128];                   // normalised centred keypoints (double buffer)
-
-  const int64_t w = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (gw >= p.n_windows * p.T) return;
+  const int64_t w = gw / p.T;
+  const int t = (int)(gw - w * p.T);
   const int vid = p.win_video[w];
   const int start = p.win_start[w];
   const int64_t f0 = p.frame_offset[vid];
   const int L = (int)(p.frame_offset[vid + 1] - f0);
   const Norm nz{p.mean, p.stdv};
-  int n_reflect = 0;
-
-  for (int t = 0; t < p.T; ++t) {
-    const int64_t cur = f0 + src_frame(start, t, L);
-    const int64_t prv = (t == 0) ? cur : f0 + src_frame(start, t - 1, L);
-    float* out = p.feats ? p.feats + ((int64_t)w * p.T + t) * p.D : nullptr;
-    __half* out16 = p.feats16 ? p.feats16 + ((int64_t)w * p.T + t) * p.D16 : nullptr;
+  const int64_t cur = f0 + src_frame(start, t, L);
+  const int64_t prv = (t == 0) ? cur : f0 + src_frame(start, t - 1, L);
+  float* out = p.feats ? p.feats + gw * p.D : nullptr;
+  __half* out16 = p.feats16 ? p.feats16 + gw * p.D16 : nullptr;
 
 #pragma unroll 1
-    for (int m = 0; m < p.M; ++m) {
-      const int dim = p.raw_dim[m];
-      const float* xc = p.src[m] + cur * dim;
-      const float* xp = p.src[m] + prv * dim;
-      const int ro = p.raw_off[m], dofs = p.diff_off[m];
-      const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
-      const int kind = p.kind[m];
+  for (int m = 0; m < p.M; ++m) {
+    const int dim = p.raw_dim[m];
+    const float* xc = p.src[m] + cur * dim;
+    const float* xp = p.src[m] + prv * dim;
+    const int ro = p.raw_off[m], dofs = p.diff_off[m];
+    const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
+    const int kind = p.kind[m];
+    const bool has_diff = p.diff_dim[m] > 0;
 
-      if (kind == TAG_KIND_COSINE) {
-        // ---- raw + sum of squares (dim <= 4*kThreads, checked on the host)
-        float x[4], xq[4];
-        float ss = 0.f;
+    if (kind == TAG_KIND_COSINE) {
+      // dim <= 1024 (checked on the host): 32 elements per lane, coalesced 128 B per warp load
+      float a[32], b[32];
+      float sa = 0.f, sb = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = tid + j * kThreads;
-          x[j] = (i < dim) ? __ldg(xc + i) : 0.f;
-          ss += x[j] * x[j];
-        }
-        ss = block_sum(ss, red);
-        const float dn = fmaxf(sqrtf(ss), 1e-12f);          // F.normalize eps
-        const float dnp = (t == 0) ? dn : s_dn[m];
-        const bool has_diff = p.diff_dim[m] > 0;
+      for (int j = 0; j < 32; ++j) {
+        const int i = lane + 32 * j;
+        a[j] = (i < dim) ? __ldg(xc + i) : 0.f;
+        b[j] = (i < dim && has_diff) ? __ldg(xp + i) : 0.f;
+        sa = fmaf(a[j], a[j], sa);
+        sb = fmaf(b[j], b[j], sb);
+      }
+      const float dn = fmaxf(sqrtf(warp_sum(sa)), 1e-12f);          // F.normalize eps
+      const float dnp = fmaxf(sqrtf(warp_sum(sb)), 1e-12f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = tid + j * kThreads;
-          xq[j] = (i < dim && has_diff && t > 0) ? __ldg(xp + i) : x[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = tid + j * kThreads;
-          if (i < dim) {
-            const float r = nz(x[j], ro + i);
-            if (out) out[ro + i] = r;
-            if (out16) out16[ro16 + i] = __float2half_rn(r);
-            if (has_diff) {
-              const float d = nz(x[j] / dn - xq[j] / dnp, dofs + i);
-              if (out) out[dofs + i] = d;
-              if (out16) out16[do16 + i] = __float2half_rn(d);
-            }
-          }
-        }
-        __syncthreads();                                    // everyone has read s_dn[m]
-        if (tid == 0) s_dn[m] = dn;
-      } else if (kind == TAG_KIND_ROTMAT) {
-        for (int i = tid; i < dim; i += kThreads) {
-          const float r = nz(__ldg(xc + i), ro + i);
+      for (int j = 0; j < 32; ++j) {
+        const int i = lane + 32 * j;
+        if (i < dim) {
+          const float r = nz(a[j], ro + i);
           if (out) out[ro + i] = r;
           if (out16) out16[ro16 + i] = __float2half_rn(r);
+          if (has_diff) {
+            const float d = nz(a[j] / dn - b[j] / dnp, dofs + i);
+            if (out) out[dofs + i] = d;
+            if (out16) out16[do16 + i] = __float2half_rn(d);
+          }
         }
-        const int J = dim / 9;
-        if (p.diff_dim[m] > 0 && tid < J) {
+      }
+    } else if (kind == TAG_KIND_ROTMAT) {
+      for (int i = lane; i < dim; i += 32) {
+        const float r = nz(__ldg(xc + i), ro + i);
+        if (out) out[ro + i] = r;
+        if (out16) out16[ro16 + i] = __float2half_rn(r);
+      }
+      const int J = dim / 9;
+      if (has_diff) {
+        for (int jn = lane; jn < J; jn += 32) {
           float R[9], Q[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) { R[k] = __ldg(xc + tid * 9 + k); Q[k] = __ldg(xp + tid * 9 + k); }
+          for (int k = 0; k < 9; ++k) { R[k] = __ldg(xc + jn * 9 + k); Q[k] = __ldg(xp + jn * 9 + k); }
           // Rrel = Q^T R  (utils.py:172), entries [i][j] = sum_k Q[k][i] R[k][j]
           float E[9];
 #pragma unroll
@@ -129,79 +123,80 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
           const float wv[3] = {theta * v0, theta * v1, theta * v2};
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const float d = nz(wv[k], dofs + tid * 3 + k);
-            if (out) out[dofs + tid * 3 + k] = d;
-            if (out16) out16[do16 + tid * 3 + k] = __float2half_rn(d);
+            const float d = nz(wv[k], dofs + jn * 3 + k);
+            if (out) out[dofs + jn * 3 + k] = d;
+            if (out16) out16[do16 + jn * 3 + k] = __float2half_rn(d);
           }
         }
-      } else if (kind == TAG_KIND_PLAIN) {
-        for (int i = tid; i < dim; i += kThreads) {
-          const float x = __ldg(xc + i);
-          const float r = nz(x, ro + i);
-          if (out) out[ro + i] = r;
-          if (out16) out16[ro16 + i] = __float2half_rn(r);
-          if (p.diff_dim[m] > 0) {
-            const float d = nz(x - __ldg(xp + i), dofs + i);
-            if (out) out[dofs + i] = d;
-            if (out16) out16[do16 + i] = __float2half_rn(d);
-          }
+      }
+    } else if (kind == TAG_KIND_PLAIN) {
+      for (int i = lane; i < dim; i += 32) {
+        const float x = __ldg(xc + i);
+        const float r = nz(x, ro + i);
+        if (out) out[ro + i] = r;
+        if (out16) out16[ro16 + i] = __float2half_rn(r);
+        if (has_diff) {
+          const float d = nz(x - __ldg(xp + i), dofs + i);
+          if (out) out[dofs + i] = d;
+          if (out16) out16[do16 + i] = __float2half_rn(d);
         }
-      } else {  // TAG_KIND_PROCRUSTES: K = dim/2 <= 64 points, handled by warp 0
-        for (int i = tid; i < dim; i += kThreads) {
-          const float r = nz(__ldg(xc + i), ro + i);
-          if (out) out[ro + i] = r;
-          if (out16) out16[ro16 + i] = __float2half_rn(r);
-        }
-        if (p.diff_dim[m] > 0 && tid < 32) {
-          const int K = dim / 2;
-          const int k0 = tid, k1 = tid + 32;
-          const bool a0 = k0 < K, a1 = k1 < K;
-          float x0 = a0 ? __ldg(xc + 2 * k0) : 0.f, y0 = a0 ? __ldg(xc + 2 * k0 + 1) : 0.f;
-          float x1 = a1 ? __ldg(xc + 2 * k1) : 0.f, y1 = a1 ? __ldg(xc + 2 * k1 + 1) : 0.f;
-          const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;   // utils.py:192
+      }
+    } else {  // TAG_KIND_PROCRUSTES: K = dim/2 <= 64 points, two per lane
+      for (int i = lane; i < dim; i += 32) {
+        const float r = nz(__ldg(xc + i), ro + i);
+        if (out) out[ro + i] = r;
+        if (out16) out16[ro16 + i] = __float2half_rn(r);
+      }
+      if (has_diff) {
+        const int K = dim / 2;
+        const int k0 = lane, k1 = lane + 32;
+        const bool a0 = k0 < K, a1 = k1 < K;
+        // centre + Frobenius-normalise one frame's points (utils.py:192-196)
+        auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
+          x0 = a0 ? __ldg(x + 2 * k0) : 0.f; y0 = a0 ? __ldg(x + 2 * k0 + 1) : 0.f;
+          x1 = a1 ? __ldg(x + 2 * k1) : 0.f; y1 = a1 ? __ldg(x + 2 * k1 + 1) : 0.f;
+          const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
           x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
           x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
-          const float sc = fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);   // :195
+          const float sc = fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
           x0 /= sc; y0 /= sc; x1 /= sc; y1 /= sc;
-          float* cb = s_kp[t & 1];
-          const float* pb = s_kp[(t & 1) ^ 1];
-          cb[2 * k0] = x0; cb[2 * k0 + 1] = y0; cb[2 * k1] = x1; cb[2 * k1 + 1] = y1;
-          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-          if (t > 0) {
-            const float px0 = pb[2 * k0], py0 = pb[2 * k0 + 1], px1 = pb[2 * k1], py1 = pb[2 * k1 + 1];
-            // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
-            const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
-            const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
-            if (h00 * h11 - h01 * h10 < 0.f) ++n_reflect;
-            const float ang = atan2f(h10 - h01, h00 + h11);
-            float sn, cs;
-            sincosf(ang, &sn, &cs);
-            // X @ R with R = [[c, s], [-s, c]]  (== Vh @ U.T for det(H) > 0)
-            d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
-            d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
-          }
-          if (a0) {
-            const float e0 = nz(d00, dofs + 2 * k0), e1 = nz(d01, dofs + 2 * k0 + 1);
-            if (out) { out[dofs + 2 * k0] = e0; out[dofs + 2 * k0 + 1] = e1; }
-            if (out16) { out16[do16 + 2 * k0] = __float2half_rn(e0); out16[do16 + 2 * k0 + 1] = __float2half_rn(e1); }
-          }
-          if (a1) {
-            const float e0 = nz(d10, dofs + 2 * k1), e1 = nz(d11, dofs + 2 * k1 + 1);
-            if (out) { out[dofs + 2 * k1] = e0; out[dofs + 2 * k1 + 1] = e1; }
-            if (out16) { out16[do16 + 2 * k1] = __float2half_rn(e0); out16[do16 + 2 * k1 + 1] = __float2half_rn(e1); }
-          }
-          __syncwarp();
+        };
+        float x0, y0, x1, y1, px0, py0, px1, py1;
+        load_norm(xc, x0, y0, x1, y1);
+        load_norm(xp, px0, py0, px1, py1);
+        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+        if (t > 0) {
+          // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
+          const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
+          const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
+          if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+          const float ang = atan2f(h10 - h01, h00 + h11);
+          float sn, cs;
+          sincosf(ang, &sn, &cs);
+          // X @ R with R = [[c, s], [-s, c]]  (== Vh @ U.T for det(H) > 0)
+          d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
+          d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
+        }
+        if (a0) {
+          const float e0 = nz(d00, dofs + 2 * k0), e1 = nz(d01, dofs + 2 * k0 + 1);
+          if (out) { out[dofs + 2 * k0] = e0; out[dofs + 2 * k0 + 1] = e1; }
+          if (out16) { out16[do16 + 2 * k0] = __float2half_rn(e0); out16[do16 + 2 * k0 + 1] = __float2half_rn(e1); }
+        }
+        if (a1) {
+          const float e0 = nz(d10, dofs + 2 * k1), e1 = nz(d11, dofs + 2 * k1 + 1);
+          if (out) { out[dofs + 2 * k1] = e0; out[dofs + 2 * k1 + 1] = e1; }
+          if (out16) { out16[do16 + 2 * k1] = __float2half_rn(e0); out16[do16 + 2 * k1 + 1] = __float2half_rn(e1); }
         }
       }
     }
   }
-  if (p.flags != nullptr && tid == 0 && n_reflect > 0) atomicAdd(p.flags, n_reflect);
 }
 
 }  // namespace
 
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
   if (p.n_windows <= 0) return cudaSuccess;
-  k_feature_fuse<<<(unsigned)p.n_windows, kThreads, 0, s>>>(p);
+  const int64_t warps = p.n_windows * p.T;
+  k_feature_fuse<<<(unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32)), kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }

@@ -54,19 +54,20 @@ class TagScorer:
         self.clip_len, self.stride = int(clip_len), int(stride)
         self.mean, self.std = stats_vectors(stats, model.modalities, self.device)
         self.model.eval()
-        self._tables: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------
     def to_device(self, vb: VideoBatch) -> DeviceVideos:
         return DeviceVideos(vb, self.model.modalities, self.device)
 
     def _table(self, dv: DeviceVideos):
-        key = (id(dv), self.clip_len, self.stride)
-        if key not in self._tables:
+        """window table of a video batch, cached ON the batch object (never keyed by id(): ids are reused)."""
+        key = (self.clip_len, self.stride)
+        cache = dv.__dict__.setdefault("_window_tables", {})
+        if key not in cache:
             wv, ws, seg = window_table(dv.lengths, self.clip_len, self.stride)
-            self._tables = {key: (torch.from_numpy(wv).to(self.device), torch.from_numpy(ws).to(self.device),
-                                  torch.from_numpy(seg).to(self.device), int(seg[-1]))}
-        return self._tables[key]
+            cache[key] = (torch.from_numpy(wv).to(self.device), torch.from_numpy(ws).to(self.device),
+                          torch.from_numpy(seg).to(self.device), int(seg[-1]))
+        return cache[key]
 
     def encode(self, dv: DeviceVideos, want_frames: bool = False):
         """-> dict(seq [N,256], tc_window [N], seg [V+1], frames [N,T+1,256]|None, flags int32[1])"""
@@ -126,7 +127,6 @@ class TagScorer:
         dv = self.to_device(vb_host)
         ac, tc = self.score(dv, centroids)
         out = torch.stack([ac, tc], 0).cpu()
-        self._tables = {}
         return out[0], out[1]
 
     def scores_dict(self, vb: VideoBatch, ac: torch.Tensor, tc: torch.Tensor) -> Dict[str, Dict[str, float]]:
