@@ -50,7 +50,8 @@ def _run_tc(M, N, K, taps, dil, T, act, use_bias, res_kind, out_kind, seed=0):
     C16 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16) if out_kind in (16, 48) else None
     C32 = torch.full((M, N), float("nan"), device=DEV) if out_kind in (32, 48) else None
     rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, W.data_ptr(), M, N, K, taps, dil, T, _lib.ptr(bias), _lib.ptr(res16),
-                               _lib.ptr(res32), _lib.ptr(C16), _lib.ptr(C32), act, torch.cuda.current_stream().cuda_stream)
+                               _lib.ptr(res32), _lib.ptr(C16), _lib.ptr(C32), act, None, None,
+                               torch.cuda.current_stream().cuda_stream)
     _lib.check(h, rc, "tag_debug_gemm_tc")
     torch.cuda.synchronize()
     res = res16.float() if res16 is not None else res32
@@ -97,9 +98,38 @@ def test_gemm_tc_rejects_unsupported_shapes():
     Cc = torch.zeros(96, 256, device=DEV, dtype=torch.float16)
     s = torch.cuda.current_stream().cuda_stream
     # T = 48 neither divides 128 nor is a multiple of it
-    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 5, 1, 48, None, None, None, Cc.data_ptr(), None, 0, s) != 0
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 5, 1, 48, None, None, None, Cc.data_ptr(), None, 0, None, None, s) != 0
     assert b"T dividing 128" in lib.tag_last_error(h)
-    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 100, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 0, s) != 0
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 100, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 0, None, None, s) != 0
+    # fused GroupNorm only for convs whose tile owns whole windows
+    g = torch.ones(256, device=DEV)
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 1, g.data_ptr(), g.data_ptr(), s) != 0
+
+
+@pytest.mark.parametrize("W_,T,dil", [(8, 32, 1), (37, 32, 8), (12, 16, 2), (5, 64, 4), (3, 128, 8), (150 * 4, 32, 2), (9, 8, 1)])
+def test_gemm_tc_fused_groupnorm(W_, T, dil):
+    """conv2 form of reference TemporalConvBlock (model.py:38-40): GroupNorm(1,256)(GELU(conv(y) + res)) in one kernel,
+    written in place over the residual buffer as the encoder does."""
+    lib = _lib.load()
+    h = tb.scoring.util_handle(DEV)
+    M, N, K, taps = W_ * T, 256, 256, 5
+    gen = torch.Generator(device=DEV).manual_seed(W_ * 1000 + T)
+    A = torch.randn(M, K, device=DEV, generator=gen).half()
+    Wt = (torch.randn(N, taps * K, device=DEV, generator=gen) / math.sqrt(K * taps)).half()
+    res = torch.randn(M, N, device=DEV, generator=gen).half()
+    gamma = 1.0 + 0.1 * torch.randn(N, device=DEV, generator=gen)
+    beta = 0.05 * torch.randn(N, device=DEV, generator=gen)
+    z = _gemm_ref(A.float(), Wt.float(), taps, dil, T, None, res.float(), 1)              # GELU(conv + res), float64
+    zz = z.reshape(W_, T * N)
+    ref = ((zz - zz.mean(1, keepdim=True)) / torch.sqrt(zz.var(1, unbiased=False, keepdim=True) + 1e-5)).reshape(M, N)
+    ref = ref * gamma.double() + beta.double()
+    buf = res.clone()                                                                       # in place: C16 == res16
+    rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, Wt.data_ptr(), M, N, K, taps, dil, T, None, buf.data_ptr(), None,
+                               buf.data_ptr(), None, 1, gamma.data_ptr(), beta.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(h, rc, "tag_debug_gemm_tc(gn)")
+    torch.cuda.synchronize()
+    err = (buf.double() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), _diag(buf, ref, f"GN W={W_} T={T}")
 
 
 @pytest.mark.parametrize("tag", ["m5_t32", "m7_t256"])

@@ -36,7 +36,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GN_RED_BYTES = 2 * EPI_WARPS * 32 * 8;     // double-buffered per-lane (sum, sumsq) exchange
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GN_RED_BYTES;
 
 // tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B,
 // N>>3 at bits 17-22, M>>4 at bits 24-28.
@@ -57,6 +58,8 @@ struct TcParams {
   __half* C16; int ldc;
   float* C32;
   int act;
+  const float* gn_gamma;   // GN instantiation only: GroupNorm(1 group) affine, fused after the activation
+  const float* gn_beta;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,6 +139,49 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// v = act(acc + bias + res) for 32 consecutive columns of one row
+__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[32], float (&v)[32], int64_t r, int n) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+    }
+  }
+  if (p.res16 != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(rp + i);
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
+    }
+  }
+  if (p.res32 != nullptr) {
+    const float4* rp = reinterpret_cast<const float4*>(p.res32 + r * (int64_t)p.N + n);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 f = __ldg(rp + i);
+      v[i * 4] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+  } else if (p.act == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+}
+
+// GN = true: the epilogue additionally applies GroupNorm(1 group, 256 channels) over each whole (T x 256) window
+// of the tile (reference model.py:32, :40) — conv2 + residual + GELU + GroupNorm in one kernel. Needs N == 256 and
+// T dividing 128 so that a tile owns whole windows; statistics are exchanged between the 2*max(1,T/32) epilogue
+// warps that share a window through shared memory and a named barrier.
+template <bool GN>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -234,69 +280,116 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       tc_fence_after();
       const int64_t r = m_tile * BLOCK_M + q * 32 + lane;
       const bool row_ok = r < p.M;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = half * 128 + c * 32;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), raw);
-        if (row_ok) {
-          const int n = n_tile * BLOCK_N + col;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128);
+      if constexpr (GN) {
+        // ---- pass 1: z = GELU(acc + res), per-row partial sums, z stashed as fp16 pairs in registers
+        uint32_t stash[64];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + (uint32_t)(c * 32), raw);
           float v[32];
+          if (row_ok) {
+            epi_values(p, raw, v, r, half * 128 + c * 32);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
-          if (p.res16 != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(rp + i);
-              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+          for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
-            }
+          for (int i = 0; i < 16; ++i) {
+            const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            stash[c * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          if (p.res32 != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(p.res32 + r * (int64_t)p.N + n);
+        }
+        // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 2 column halves
+        const int width = p.T < 32 ? p.T : 32;
+        for (int o = width >> 1; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(FULL_MASK, s1, o);
+          s2 += __shfl_xor_sync(FULL_MASK, s2, o);
+        }
+        const int G = p.T > 32 ? p.T / 32 : 1;
+        const uint32_t red = bar_base + 256u + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q / G), "r"(2 * G * 32) : "memory");
+        float S1 = 0.f, S2 = 0.f;
+        for (int qq = 0; qq < G; ++qq) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 f = __ldg(rp + i);
-              v[i * 4] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
-            }
+          for (int hh = 0; hh < 2; ++hh) {
+            const int e = hh * 4 + ((((q / G) * G + qq) - 2) & 3);
+            float a, b;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)((e * 32 + lane) * 8)) : "memory");
+            S1 += a; S2 += b;
           }
-          if (p.act == 1) {
+        }
+        const float inv_n = 1.0f / ((float)p.T * (float)BLOCK_N);
+        const float mean = S1 * inv_n;
+        const float var = fmaxf(S2 * inv_n - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        // ---- pass 2: normalise the stash, per-channel affine, store fp16
+        if (row_ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
-          } else if (p.act == 2) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.C16 != nullptr) {
+          for (int c = 0; c < 4; ++c) {
+            const int n = half * 128 + c * 32;
             uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               uint4 u;
               __half2* hh = reinterpret_cast<__half2*>(&u);
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + n + i * 8));
+              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + n + i * 8 + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + n + i * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + n + i * 8 + 4));
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+              for (int e = 0; e < 4; ++e) {
+                const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&stash[c * 16 + i * 4 + e]));
+                hh[e] = __floats2half2_rn(fmaf((z.x - mean) * rstd, gg[2 * e], bb[2 * e]),
+                                          fmaf((z.y - mean) * rstd, gg[2 * e + 1], bb[2 * e + 1]));
+              }
               op[i] = u;
             }
           }
-          if (p.C32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(p.C32 + r * (int64_t)p.N + n);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col = half * 128 + c * 32;
+          uint32_t raw[32];
+          tmem_ld32(t_row + (uint32_t)(c * 32), raw);
+          if (row_ok) {
+            const int n = n_tile * BLOCK_N + col;
+            float v[32];
+            epi_values(p, raw, v, r, n);
+            if (p.C16 != nullptr) {
+              uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+              for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+                op[i] = u;
+              }
+            }
+            if (p.C32 != nullptr) {
+              float4* op = reinterpret_cast<float4*>(p.C32 + r * (int64_t)p.N + n);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
 
@@ -332,7 +425,8 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-  e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
     delete c;
@@ -362,6 +456,13 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   TcParams p{};
   p.M = g.M; p.N = g.N; p.kb_per_tap = g.K / BLOCK_K; p.taps = g.taps; p.dil = g.dil; p.T = g.T;
   p.bias = g.bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
+  p.gn_gamma = g.gn_gamma; p.gn_beta = g.gn_beta;
+  const bool gn = g.gn_gamma != nullptr;
+  if (gn) {
+    if (g.gn_beta == nullptr || g.taps <= 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 != nullptr || g.T > BLOCK_M ||
+        (g.T & (g.T - 1)) != 0)
+      return bad("fused GroupNorm needs a conv with N == 256, fp16 output and T a power of two <= 128");
+  }
   p.n_tiles = g.N / BLOCK_N;
   p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
 
@@ -404,6 +505,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
 
   const int64_t total = p.m_tiles * p.n_tiles;
   const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
-  k_gemm_tc<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  if (gn) k_gemm_tc<true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  else k_gemm_tc<false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
   return cudaGetLastError();
 }

@@ -102,6 +102,8 @@ struct GemmTC {
   __half* C16; int ldc;           // fp16 output or null
   float* C32;                     // fp32 output or null (ld = N)
   int act;
+  const float* gn_gamma;          // non-null: fuse GroupNorm(1,256) over each (T x 256) window after the activation
+  const float* gn_beta;
 };
 struct TcContext;   // opaque: driver entry points + cached tensor maps
 TcContext* tc_context_create(int device, char* err, int errlen);

@@ -322,9 +322,18 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
         c1.T = T; c1.C16 = bufY1; c1.ldc = kD; c1.act = 1;
         rc = gemm_tc_run(h, s, c1, 2.0 * R * kD * kD * kk); if (rc) return rc;
         GemmTC c2 = c1;
-        c2.A = bufY1; c2.W = e.conv16[b][1]; c2.res16 = bufH; c2.ldr = kD; c2.C16 = bufY2;
-        rc = gemm_tc_run(h, s, c2, 2.0 * R * kD * kD * kk); if (rc) return rc;
-        { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_groupnorm<__half>(bufY2, e.gn_g[b], e.gn_b[b], bufH, W, T, s)); }
+        c2.A = bufY1; c2.W = e.conv16[b][1]; c2.res16 = bufH; c2.ldr = kD;
+        const bool fuse_gn = T <= 128 && (T & (T - 1)) == 0;
+        if (fuse_gn) {
+          // conv2 + residual + GELU + GroupNorm in one kernel; in place over the residual (a thread reads and
+          // later overwrites only its own row/column block)
+          c2.C16 = bufH; c2.gn_gamma = e.gn_g[b]; c2.gn_beta = e.gn_b[b];
+          rc = gemm_tc_run(h, s, c2, 2.0 * R * kD * kD * kk); if (rc) return rc;
+        } else {
+          c2.C16 = bufY2;
+          rc = gemm_tc_run(h, s, c2, 2.0 * R * kD * kD * kk); if (rc) return rc;
+          { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_groupnorm<__half>(bufY2, e.gn_g[b], e.gn_b[b], bufH, W, T, s)); }
+        }
       }
       __half* P = (__half*)h->P[e_idx++];
       GemmTC pj{};
@@ -807,7 +816,7 @@ int tag_debug_gemm_f32(tag_handle* h, const float* A, int32_t lda, const float* 
 
 int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, int64_t M, int32_t N, int32_t K,
                       int32_t taps, int32_t dil, int32_t T, const float* bias, const void* res16, const float* res32,
-                      void* C16, float* C32, int32_t act, void* stream) {
+                      void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta, void* stream) {
   if (!h) return TAG_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if (!h->tc) {
@@ -817,6 +826,7 @@ int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, 
   GemmTC g{};
   g.A = (const __half*)A; g.M = M; g.lda = lda; g.W = (const __half*)W; g.N = N; g.K = K; g.taps = taps; g.dil = dil; g.T = T;
   g.bias = bias; g.res16 = (const __half*)res16; g.ldr = N; g.res32 = res32; g.C16 = (__half*)C16; g.ldc = N; g.C32 = C32; g.act = act;
+  g.gn_gamma = gn_gamma; g.gn_beta = gn_beta;
   h->err[0] = 0;
   return gemm_tc_run(h, (cudaStream_t)stream, g, 2.0 * (double)M * N * K * taps);
 }
