@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -29,19 +30,28 @@
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 64, UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
-constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;       // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// 1-CTA tiles: the CTA stages all 256 weight rows (32 KiB) -> 4 stages of 48 KiB.
+// CTA pairs (cta_group::2): each CTA stages its own 128 activation rows and HALF of the weight rows (16 KiB), the
+// pair's tcgen05.mma reads both halves -> 6 stages of 32 KiB and 1/3 less L2->SM traffic per FLOP.
+template <bool PAIR> struct Cfg {
+  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
+};
+constexpr int MAX_BARS = 2 * 6 + 4;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int GN_RED_BYTES = 2 * EPI_WARPS * 32 * 8;     // double-buffered per-lane (sum, sumsq) exchange
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GN_RED_BYTES;
+constexpr int RING_BYTES = 4 * (A_BYTES + BLOCK_N * BLOCK_K * 2);      // == 6 * 32 KiB
+constexpr int GN_AFFINE_BYTES = 2 * BLOCK_N * 4;           // gamma[256] || beta[256]
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GN_RED_BYTES + GN_AFFINE_BYTES;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> the pair's leader CTA
 
-// tcgen05 instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B,
-// N>>3 at bits 17-22, M>>4 at bits 24-28.
-constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// tcgen05 instruction descriptor (Cfg::IDESC), kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B,
+// N>>3 at bits 17-22, M>>4 at bits 24-28 (M = 256 for a CTA pair).
 
 struct TcParams {
   int64_t M;
@@ -106,6 +116,47 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// CTA-pair variants (executed by both CTAs; the mbarrier is the LEADER CTA's)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "l"(kEvictNormal)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "l"(kEvictNormal)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 // shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows 128 B apart, 8-row groups
 // 1024 B apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -126,7 +177,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -136,11 +187,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// tcgen05.wait::ld with the loaded registers as in/out operands, so no consumer can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
+// fp16 residual of 32 consecutive columns of one row, issued early so its L2 latency hides behind the accumulator wait
+__device__ __forceinline__ void load_res16(const TcParams& p, uint4 (&dst)[4], int64_t r, int n, bool row_ok) {
+  if (p.res16 != nullptr && row_ok) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = __ldg(rp + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // v = act(acc + bias + res) for 32 consecutive columns of one row
-__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[32], float (&v)[32], int64_t r, int n) {
+__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[32], const uint4 (&res)[4], float (&v)[32], int64_t r, int n) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
   if (p.bias != nullptr) {
@@ -151,11 +222,9 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
     }
   }
   if (p.res16 != nullptr) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint4 u = __ldg(rp + i);
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+      const __half2* hh = reinterpret_cast<const __half2*>(&res[i]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
     }
@@ -181,46 +250,70 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
 // of the tile (reference model.py:32, :40) — conv2 + residual + GELU + GroupNorm in one kernel. Needs N == 256 and
 // T dividing 128 so that a tile owns whole windows; statistics are exchanged between the 2*max(1,T/32) epilogue
 // warps that share a window through shared memory and a named barrier.
-template <bool GN>
+//
+// PAIR = true: the kernel is launched in clusters of two CTAs that form one cta_group::2 MMA (M = 256: each CTA owns
+// 128 rows of the tile and their accumulators in its own TMEM). Each CTA's producer loads its 128 activation rows and
+// its half of the weight rows; all TMA bytes are counted on the leader CTA's full barrier; the leader's elected thread
+// issues the MMAs and its commits are multicast to the empty / accumulator-full barriers of both CTAs; the peer's
+// epilogue warps release accumulators on the leader's barrier.
+template <bool GN, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  constexpr int STAGES = Cfg<PAIR>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B needs 1024 B alignment
-  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bar_base = smem_base + RING_BYTES;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * MAX_BARS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_gb = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + GN_RED_BYTES);
+  if constexpr (GN) {
+    for (int i = threadIdx.x; i < BLOCK_N; i += THREADS) { s_gb[i] = __ldg(p.gn_gamma + i); s_gb[BLOCK_N + i] = __ldg(p.gn_beta + i); }
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (this kernel runs one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int n_kb = p.taps * p.kb_per_tap;
-  const int64_t total_tiles = p.m_tiles * p.n_tiles;
+  // work items: (m-tile, n-tile) per CTA, or (pair of m-tiles, n-tile) per cluster
+  const int64_t total_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+  const int64_t tile0 = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t tile_step = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  auto m_tile_of = [&](int64_t tile) { const int64_t mt = tile / p.n_tiles; return PAIR ? mt * 2 + rank : mt; };
 
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer =================
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int64_t m_tile = tile / p.n_tiles;
-        const int n_tile = (int)(tile - m_tile * p.n_tiles);
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int64_t m_tile = m_tile_of(tile);
+        const int n_tile = (int)(tile % p.n_tiles);
         int c1_base, c2;
         if (p.mode == 0) { c1_base = (int)(m_tile * BLOCK_M); c2 = 0; }
         else if (p.mode == 1) { c1_base = 0; c2 = (int)(m_tile * p.wpt); }
@@ -230,20 +323,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const int kc = kb - j * p.kb_per_tap;
           const int shift = (p.taps > 1) ? (j - p.taps / 2) * p.dil : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
-          tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+          if constexpr (PAIR) {
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);       // bytes of both CTAs
+            tma_load_3d_pair(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+            tma_load_2d_pair(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+            tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+            tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
+    if (lane == 0 && leader) {
+      // ================= MMA issuer (leader CTA of a pair) =================
       int stage = 0; uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);           // epilogue has drained this accumulator
@@ -258,12 +357,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));                      // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));                          // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
       }
     }
   } else {
@@ -271,15 +373,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;       // which 128 accumulator columns
     int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int64_t m_tile = tile / p.n_tiles;
-      const int n_tile = (int)(tile - m_tile * p.n_tiles);
+    for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int64_t m_tile = m_tile_of(tile);
+      const int n_tile = (int)(tile % p.n_tiles);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int64_t r = m_tile * BLOCK_M + q * 32 + lane;
       const bool row_ok = r < p.M;
+      const int n_base = n_tile * BLOCK_N + half * 128;
+      uint4 res_cur[4];
+      load_res16(p, res_cur, r, n_base, row_ok);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128);
       if constexpr (GN) {
         // ---- pass 1: z = GELU(acc + res), per-row partial sums, z stashed as fp16 pairs in registers
@@ -288,10 +393,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t raw[32];
-          tmem_ld32(t_row + (uint32_t)(c * 32), raw);
+          tmem_ld32_issue(t_row + (uint32_t)(c * 32), raw);
+          uint4 res_next[4];
+          if (c < 3) load_res16(p, res_next, r, n_base + (c + 1) * 32, row_ok);
+          tmem_ld32_wait(raw);
           float v[32];
           if (row_ok) {
-            epi_values(p, raw, v, r, half * 128 + c * 32);
+            epi_values(p, raw, res_cur, v, r, n_base + c * 32);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -303,11 +411,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
             stash[c * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
           }
+          if (c < 3) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
+          }
         }
         // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp now
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
         // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 2 column halves
         const int width = p.T < 32 ? p.T : 32;
         for (int o = width >> 1; o > 0; o >>= 1) {
@@ -342,10 +454,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             for (int i = 0; i < 4; ++i) {
               uint4 u;
               __half2* hh = reinterpret_cast<__half2*>(&u);
-              const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + n + i * 8));
-              const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + n + i * 8 + 4));
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + n + i * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + n + i * 8 + 4));
+              const float4 g0 = *reinterpret_cast<const float4*>(s_gb + n + i * 8);
+              const float4 g1 = *reinterpret_cast<const float4*>(s_gb + n + i * 8 + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + n + i * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + n + i * 8 + 4);
               const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -359,15 +471,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           }
         }
       } else {
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int col = half * 128 + c * 32;
           uint32_t raw[32];
-          tmem_ld32(t_row + (uint32_t)(c * 32), raw);
+          tmem_ld32_issue(t_row + (uint32_t)(c * 32), raw);
+          uint4 res_next[4];
+          if (c < 3) load_res16(p, res_next, r, n_base + (c + 1) * 32, row_ok);
+          tmem_ld32_wait(raw);
           if (row_ok) {
-            const int n = n_tile * BLOCK_N + col;
+            const int n = n_base + c * 32;
             float v[32];
-            epi_values(p, raw, v, r, n);
+            epi_values(p, raw, res_cur, v, r, n);
             if (p.C16 != nullptr) {
               uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
 #pragma unroll
@@ -385,19 +499,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
             }
           }
+          if (c < 3) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
+          }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // no CTA exits (or frees TMEM) while its partner may still signal / read it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -410,6 +530,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TcContext {
   EncodeTiledFn encode = nullptr;
   int num_sms = 148;
+  bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
 };
 
 TcContext* tc_context_create(int device, char* err, int errlen) {
@@ -425,8 +546,12 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-  e = cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(k_gemm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  const char* env = getenv("TAG_TC_PAIR");
+  if (env != nullptr) c->pair = env[0] != '0';
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
     delete c;
@@ -496,16 +621,32 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   const int64_t ktot = (int64_t)g.taps * g.K;
   cuuint64_t bdim[2] = {(cuuint64_t)ktot, (cuuint64_t)g.N};
   cuuint64_t bstr[1] = {(cuuint64_t)ktot * 2};
-  cuuint32_t bbox[2] = {BLOCK_K, BLOCK_N};
+  const bool pair = ctx->pair && p.m_tiles >= 2;
+  cuuint32_t bbox[2] = {BLOCK_K, (cuuint32_t)(pair ? BLOCK_N / 2 : BLOCK_N)};
   cuuint32_t bes[2] = {1, 1};
   r = ctx->encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(g.W), bdim, bstr, bbox, bes,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(W) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
 
+  if (pair) {
+    const int64_t total = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int64_t clusters = total < ctx->num_sms / 2 ? total : ctx->num_sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<true, true>, map_a, map_b, p);
+    return cudaLaunchKernelEx(&cfg, k_gemm_tc<false, true>, map_a, map_b, p);
+  }
   const int64_t total = p.m_tiles * p.n_tiles;
   const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
-  if (gn) k_gemm_tc<true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
-  else k_gemm_tc<false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  if (gn) k_gemm_tc<true, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  else k_gemm_tc<false, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
   return cudaGetLastError();
 }

@@ -476,7 +476,7 @@ int tag_create(tag_handle** out, const tag_config* cfg) {
     const int rd = cfg->raw_dims[m], dd = cfg->diff_dims[m], k = cfg->kinds[m];
     if (rd < 1 || dd < 0) return fail(nullptr, TAG_ERR_INVALID, "modality %d: raw_dim=%d diff_dim=%d", m, rd, dd);
     bool ok = true;
-    if (k == TAG_KIND_COSINE) ok = rd <= 1024 && (dd == 0 || dd == rd);
+    if (k == TAG_KIND_COSINE) ok = rd <= 1024 && rd % 2 == 0 && (dd == 0 || dd == rd);
     else if (k == TAG_KIND_ROTMAT) ok = rd % 9 == 0 && rd / 9 <= 256 && (dd == 0 || dd == rd / 3);
     else if (k == TAG_KIND_PLAIN) ok = (dd == 0 || dd == rd);
     else if (k == TAG_KIND_PROCRUSTES) ok = rd % 2 == 0 && rd <= 128 && (dd == 0 || dd == rd);
