@@ -41,7 +41,9 @@ template <bool PAIR> struct Cfg {
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
 };
 constexpr int MAX_BARS = 2 * 6 + 4;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                 // 4 per TMEM lane quarter, 64 accumulator columns each
+constexpr int EPI_COLS = BLOCK_N / (EPI_WARPS / 4);   // 64
+constexpr int CW = 16;                        // columns per tcgen05.ld chunk
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int GN_RED_BYTES = 2 * EPI_WARPS * 32 * 8;     // double-buffered per-lane (sum, sumsq) exchange
@@ -177,53 +179,46 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
 // tcgen05.wait::ld with the loaded registers as in/out operands, so no consumer can be scheduled above the wait
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :: "memory");
 }
 
-// fp16 residual of 32 consecutive columns of one row, issued early so its L2 latency hides behind the accumulator wait
-__device__ __forceinline__ void load_res16(const TcParams& p, uint4 (&dst)[4], int64_t r, int n, bool row_ok) {
+// fp16 residual of CW consecutive columns of one row, issued early so its L2 latency hides behind the accumulator wait
+__device__ __forceinline__ void load_res16(const TcParams& p, uint4 (&dst)[2], int64_t r, int n, bool row_ok) {
   if (p.res16 != nullptr && row_ok) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = __ldg(rp + i);
+    dst[0] = __ldg(rp); dst[1] = __ldg(rp + 1);
   } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    dst[0] = make_uint4(0u, 0u, 0u, 0u); dst[1] = dst[0];
   }
 }
 
-// v = act(acc + bias + res) for 32 consecutive columns of one row
-__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[32], const uint4 (&res)[4], float (&v)[32], int64_t r, int n) {
+// v = act(acc + bias + res) for CW consecutive columns of one row
+__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[CW], const uint4 (&res)[2], float (&v)[CW], int64_t r, int n) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
   if (p.bias != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
+    for (int i = 0; i < CW; i += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
       v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
   }
   if (p.res16 != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       const __half2* hh = reinterpret_cast<const __half2*>(&res[i]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
@@ -232,17 +227,17 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
   if (p.res32 != nullptr) {
     const float4* rp = reinterpret_cast<const float4*>(p.res32 + r * (int64_t)p.N + n);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < CW / 4; ++i) {
       const float4 f = __ldg(rp + i);
       v[i * 4] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
     }
   }
   if (p.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+    for (int i = 0; i < CW; ++i) v[i] = gelu_fast(v[i]);
   } else if (p.act == 2) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
   }
 }
 
@@ -370,8 +365,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   } else {
     // ================= epilogue warps =================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // which 128 accumulator columns
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2;          // which 64 accumulator columns
+    constexpr int NCH = EPI_COLS / CW;         // 4 chunks of 16 columns
     int64_t it = 0;
     for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int64_t m_tile = m_tile_of(tile);
@@ -380,47 +376,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int64_t r = m_tile * BLOCK_M + q * 32 + lane;
       const bool row_ok = r < p.M;
-      const int n_base = n_tile * BLOCK_N + half * 128;
-      uint4 res_cur[4];
+      const int n_base = n_tile * BLOCK_N + part * EPI_COLS;
+      uint4 res_cur[2];
       load_res16(p, res_cur, r, n_base, row_ok);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * 128);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + part * EPI_COLS);
       if constexpr (GN) {
         // ---- pass 1: z = GELU(acc + res), per-row partial sums, z stashed as fp16 pairs in registers
-        uint32_t stash[64];
+        uint32_t stash[EPI_COLS / 2];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          tmem_ld32_issue(t_row + (uint32_t)(c * 32), raw);
-          uint4 res_next[4];
-          if (c < 3) load_res16(p, res_next, r, n_base + (c + 1) * 32, row_ok);
-          tmem_ld32_wait(raw);
-          float v[32];
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
+          uint4 res_next[2];
+          if (c + 1 < NCH) load_res16(p, res_next, r, n_base + (c + 1) * CW, row_ok);
+          tmem_ld16_wait(raw);
+          float v[CW];
           if (row_ok) {
-            epi_values(p, raw, res_cur, v, r, n_base + c * 32);
+            epi_values(p, raw, res_cur, v, r, n_base + c * CW);
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int i = 0; i < CW; ++i) v[i] = 0.f;
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+          for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < CW / 2; ++i) {
             const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            stash[c * 16 + i] = *reinterpret_cast<const uint32_t*>(&h2);
+            stash[c * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&h2);
           }
-          if (c < 3) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
-          }
+          if (c + 1 < NCH) { res_cur[0] = res_next[0]; res_cur[1] = res_next[1]; }
         }
         // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp now
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
-        // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 2 column halves
+        // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 4 column parts
         const int width = p.T < 32 ? p.T : 32;
         for (int o = width >> 1; o > 0; o >>= 1) {
           s1 += __shfl_xor_sync(FULL_MASK, s1, o);
@@ -429,12 +422,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int G = p.T > 32 ? p.T / 32 : 1;
         const uint32_t red = bar_base + 256u + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + q / G), "r"(2 * G * 32) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q / G), "r"(4 * G * 32) : "memory");
         float S1 = 0.f, S2 = 0.f;
         for (int qq = 0; qq < G; ++qq) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int e = hh * 4 + ((((q / G) * G + qq) - 2) & 3);
+          for (int pp = 0; pp < EPI_WARPS / 4; ++pp) {
+            const int e = pp * 4 + ((((q / G) * G + qq) - 2) & 3);
             float a, b;
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)((e * 32 + lane) * 8)) : "memory");
             S1 += a; S2 += b;
@@ -444,48 +437,46 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const float mean = S1 * inv_n;
         const float var = fmaxf(S2 * inv_n - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
-        // ---- pass 2: normalise the stash, per-channel affine, store fp16
+        const float nmr = -mean * rstd;
+        // ---- pass 2: normalise the stash, per-channel affine (from shared memory), store fp16
         if (row_ok) {
+          const int nl = part * EPI_COLS;
+          uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + nl);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int n = half * 128 + c * 32;
-            uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
+          for (int i = 0; i < EPI_COLS / 8; ++i) {
+            uint4 u;
+            __half2* hh = reinterpret_cast<__half2*>(&u);
+            const float4 g0 = *reinterpret_cast<const float4*>(s_gb + nl + i * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(s_gb + nl + i * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + nl + i * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + nl + i * 8 + 4);
+            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              __half2* hh = reinterpret_cast<__half2*>(&u);
-              const float4 g0 = *reinterpret_cast<const float4*>(s_gb + n + i * 8);
-              const float4 g1 = *reinterpret_cast<const float4*>(s_gb + n + i * 8 + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + n + i * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + n + i * 8 + 4);
-              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&stash[c * 16 + i * 4 + e]));
-                hh[e] = __floats2half2_rn(fmaf((z.x - mean) * rstd, gg[2 * e], bb[2 * e]),
-                                          fmaf((z.y - mean) * rstd, gg[2 * e + 1], bb[2 * e + 1]));
-              }
-              op[i] = u;
+            for (int e = 0; e < 4; ++e) {
+              const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&stash[i * 4 + e]));
+              hh[e] = __floats2half2_rn(fmaf(fmaf(z.x, rstd, nmr), gg[2 * e], bb[2 * e]),
+                                        fmaf(fmaf(z.y, rstd, nmr), gg[2 * e + 1], bb[2 * e + 1]));
             }
+            op[i] = u;
           }
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t raw[32];
-          tmem_ld32_issue(t_row + (uint32_t)(c * 32), raw);
-          uint4 res_next[4];
-          if (c < 3) load_res16(p, res_next, r, n_base + (c + 1) * 32, row_ok);
-          tmem_ld32_wait(raw);
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
+          uint4 res_next[2];
+          if (c + 1 < NCH) load_res16(p, res_next, r, n_base + (c + 1) * CW, row_ok);
+          tmem_ld16_wait(raw);
           if (row_ok) {
-            const int n = n_base + c * 32;
-            float v[32];
+            const int n = n_base + c * CW;
+            float v[CW];
             epi_values(p, raw, res_cur, v, r, n);
             if (p.C16 != nullptr) {
               uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
+              for (int i = 0; i < CW / 8; ++i) {
                 uint4 u;
                 __half2* hh = reinterpret_cast<__half2*>(&u);
 #pragma unroll
@@ -496,13 +487,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (p.C32 != nullptr) {
               float4* op = reinterpret_cast<float4*>(p.C32 + r * (int64_t)p.N + n);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+              for (int i = 0; i < CW / 4; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
             }
           }
-          if (c < 3) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) res_cur[i] = res_next[i];
-          }
+          if (c + 1 < NCH) { res_cur[0] = res_next[0]; res_cur[1] = res_next[1]; }
         }
         tc_fence_before();
         __syncwarp();
