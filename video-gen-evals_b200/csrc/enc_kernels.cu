@@ -228,6 +228,152 @@ __global__ void __launch_bounds__(640) k_attention(const TA* __restrict__ qkv, T
   }
 }
 
+// ---------------------------------------------------------------- self-attention on mma.sync fragments (S <= 48)
+// One warp per (window, head): Q, K (row-major, padded to 48 x 40 halfs) and V^T (32 x 56 halfs) staged in shared
+// memory, S = Q K^T as 3 x 6 tiles of m16n8k16 (fp16 in, fp32 accumulate), softmax on the accumulator fragments
+// (row statistics via quad shuffles, exp2 domain), P re-used in registers as the A operand of P V (3 x 4 tiles).
+// 72 tensor instructions replace ~4.7k scalar-FMA warp instructions per (window, head). Attention is 0.03 % of the
+// encoder's FLOPs, so the legacy warp-level MMA is the right tool here; the GEMM-shaped 99.9 % runs on tcgen05.
+constexpr int kAttS = 48, kQStride = 40, kVStride = 56;
+constexpr int kAttWarpHalfs = 2 * kAttS * kQStride + 32 * kVStride;      // Q + K + V^T per warp
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict__ qkv, __half* __restrict__ out,
+                                                       int64_t n_pairs, int S, int n_heads) {
+  extern __shared__ __align__(16) __half smh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * 4 + warp;          // (window, head)
+  if (pair >= n_pairs) return;
+  const int64_t n = pair / n_heads;
+  const int h = (int)(pair - n * n_heads);
+  __half* sQ = smh + (size_t)warp * kAttWarpHalfs;
+  __half* sK = sQ + kAttS * kQStride;
+  __half* sVt = sK + kAttS * kQStride;
+  // zero (padding rows / keys must be exact zeros), then fill
+  for (int i = lane; i < kAttWarpHalfs / 8; i += 32) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncwarp();
+  const __half* base = qkv + n * (int64_t)S * (3 * kD) + h * 32;
+  for (int u = lane; u < S * 4; u += 32) {
+    const int row = u >> 2, part = u & 3;
+    const __half* src = base + (int64_t)row * (3 * kD) + part * 8;
+    *reinterpret_cast<uint4*>(sQ + row * kQStride + part * 8) = __ldg(reinterpret_cast<const uint4*>(src));
+    *reinterpret_cast<uint4*>(sK + row * kQStride + part * 8) = __ldg(reinterpret_cast<const uint4*>(src + kD));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + 2 * kD));
+    const __half* vh = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sVt[(part * 8 + e) * kVStride + row] = vh[e];
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, tig = lane & 3;
+  // ---- S = Q K^T : acc[mt][nt][4]
+  float sc[3][6][4];
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t bk[6][2];
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      const __half* kp = sK + (nt * 8 + g) * kQStride + ks * 16 + 2 * tig;
+      bk[nt][0] = *reinterpret_cast<const uint32_t*>(kp);
+      bk[nt][1] = *reinterpret_cast<const uint32_t*>(kp + 8);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+      uint32_t a[4];
+      const __half* qp = sQ + (mt * 16 + g) * kQStride + ks * 16 + 2 * tig;
+      a[0] = *reinterpret_cast<const uint32_t*>(qp);
+      a[1] = *reinterpret_cast<const uint32_t*>(qp + 8 * kQStride);
+      a[2] = *reinterpret_cast<const uint32_t*>(qp + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(qp + 8 * kQStride + 8);
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) mma_16816(sc[mt][nt], a, bk[nt]);
+    }
+  }
+  // ---- softmax over keys (columns): row g uses elements [0],[1]; row g+8 uses [2],[3]
+  const float scale = 0.17677669529663688110f * 1.4426950408889634f;      // log2(e) / sqrt(32)
+  uint32_t pa[3][3][4];        // P as A fragments: [mt][kt][4]
+  float inv_sum[3][2];
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt) {
+    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      const int c0 = nt * 8 + 2 * tig;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = c0 + (e & 1);
+        sc[mt][nt][e] = (col < S) ? sc[mt][nt][e] * scale : -CUDART_INF_F;
+      }
+      mx0 = fmaxf(mx0, fmaxf(sc[mt][nt][0], sc[mt][nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[mt][nt][2], sc[mt][nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) {
+      sc[mt][nt][0] = exp2f(sc[mt][nt][0] - mx0); sc[mt][nt][1] = exp2f(sc[mt][nt][1] - mx0);
+      sc[mt][nt][2] = exp2f(sc[mt][nt][2] - mx1); sc[mt][nt][3] = exp2f(sc[mt][nt][3] - mx1);
+      s0 += sc[mt][nt][0] + sc[mt][nt][1];
+      s1 += sc[mt][nt][2] + sc[mt][nt][3];
+    }
+    s0 += __shfl_xor_sync(FULL_MASK, s0, 1); s0 += __shfl_xor_sync(FULL_MASK, s0, 2);
+    s1 += __shfl_xor_sync(FULL_MASK, s1, 1); s1 += __shfl_xor_sync(FULL_MASK, s1, 2);
+    inv_sum[mt][0] = 1.0f / s0; inv_sum[mt][1] = 1.0f / s1;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      __half2 t;
+      t = __floats2half2_rn(sc[mt][2 * kt][0], sc[mt][2 * kt][1]);         pa[mt][kt][0] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(sc[mt][2 * kt][2], sc[mt][2 * kt][3]);         pa[mt][kt][1] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(sc[mt][2 * kt + 1][0], sc[mt][2 * kt + 1][1]); pa[mt][kt][2] = *reinterpret_cast<uint32_t*>(&t);
+      t = __floats2half2_rn(sc[mt][2 * kt + 1][2], sc[mt][2 * kt + 1][3]); pa[mt][kt][3] = *reinterpret_cast<uint32_t*>(&t);
+    }
+  }
+  // ---- O = P V : B[k = key][n = d] = V[key][d] = Vt[d][key]
+  float o[3][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nd][e] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      uint32_t bv[2];
+      const __half* vp = sVt + (nd * 8 + g) * kVStride + kt * 16 + 2 * tig;
+      bv[0] = *reinterpret_cast<const uint32_t*>(vp);
+      bv[1] = *reinterpret_cast<const uint32_t*>(vp + 8);
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) mma_16816(o[mt][nd], pa[mt][kt], bv);
+    }
+  }
+  // ---- store rows < S
+  __half* ob = out + n * (int64_t)S * kD + h * 32;
+#pragma unroll
+  for (int mt = 0; mt < 3; ++mt) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      const int col = nd * 8 + 2 * tig;
+      if (r0 < S) *reinterpret_cast<__half2*>(ob + (int64_t)r0 * kD + col) = __floats2half2_rn(o[mt][nd][0] * inv_sum[mt][0], o[mt][nd][1] * inv_sum[mt][0]);
+      if (r1 < S) *reinterpret_cast<__half2*>(ob + (int64_t)r1 * kD + col) = __floats2half2_rn(o[mt][nd][2] * inv_sum[mt][1], o[mt][nd][3] * inv_sum[mt][1]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm with affine
 template <typename TA>
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -330,9 +476,19 @@ static cudaError_t launch_attention_hpc(const TA* qkv, TA* out, int64_t n_window
   return cudaGetLastError();
 }
 
+static cudaError_t launch_attention_mma(const __half* qkv, __half* out, int64_t n_windows, int S, int n_heads, cudaStream_t s) {
+  const int64_t pairs = n_windows * n_heads;
+  const size_t smem = (size_t)4 * kAttWarpHalfs * sizeof(__half);
+  k_attention_mma<<<(unsigned)((pairs + 3) / 4), 128, smem, s>>>(qkv, out, pairs, S, n_heads);
+  return cudaGetLastError();
+}
+
 template <typename TA>
 cudaError_t launch_attention(const TA* qkv, TA* out, int64_t n_windows, int S, int n_heads, cudaStream_t s) {
   if (n_windows <= 0) return cudaSuccess;
+  if constexpr (sizeof(TA) == 2) {
+    if (S <= kAttS) return launch_attention_mma(qkv, out, n_windows, S, n_heads, s);
+  }
   // largest head group whose K/V fit comfortably in shared memory
   auto fits = [&](int hpc) { return n_heads % hpc == 0 && (size_t)2 * S * hpc * kHeadPad * sizeof(float) <= 160 * 1024; };
   if (fits(8)) return launch_attention_hpc<TA, 8>(qkv, out, n_windows, S, n_heads, s);
