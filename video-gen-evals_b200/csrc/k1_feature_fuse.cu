@@ -29,16 +29,29 @@ __device__ __forceinline__ int src_frame(int start, int t, int L) {
   return f < L - 1 ? f : L - 1;
 }
 
+// z-score as one FMA per element: (x - mean) / (std + 1e-6) == x * scale + shift with scale = 1/(std+1e-6) and
+// shift = -mean*scale, tabulated once per call by k_zscore_table (an IEEE division sequence per output element made
+// this HBM-bound kernel instruction-bound: ncu counted 1.9e9 warp instructions per 12.5k windows).
 struct Norm {
-  const float* mean;
-  const float* stdv;
+  const float* scale;
+  const float* shift;
   __device__ __forceinline__ float operator()(float x, int col) const {
-    if (mean == nullptr) return x;
-    // (x-mean)/(std+1e-6) with the reciprocal on the MUFU pipe (<= 2 ulp): an IEEE division sequence per output
-    // element made this HBM-bound kernel instruction-bound (ncu: 1.9e9 warp instructions per 12.5k windows)
-    return __fdividef(x - __ldg(mean + col), __ldg(stdv + col) + kEpsStd);
+    if (scale == nullptr) return x;
+    return fmaf(x, __ldg(scale + col), __ldg(shift + col));
   }
 };
+
+__global__ void k_zscore_table(const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ scale,
+                               float* __restrict__ shift, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D) {
+    const float sc = 1.0f / (stdv[i] + kEpsStd);
+    scale[i] = sc;
+    shift[i] = -mean[i] * sc;
+  }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // One warp per (window, frame): every reduction (cosine norms, keypoint centre / scale / 2x2 correlation) is a
 // warp shuffle, so there is no block barrier and no shared memory; the previous frame's quantities are recomputed
@@ -54,9 +67,18 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
   const int start = p.win_start[w];
   const int64_t f0 = p.frame_offset[vid];
   const int L = (int)(p.frame_offset[vid + 1] - f0);
-  const Norm nz{p.mean, p.stdv};
+  const Norm nz{p.mean, p.stdv};          // (scale, shift) tables when stats are given
   const int64_t cur = f0 + src_frame(start, t, L);
   const int64_t prv = (t == 0) ? cur : f0 + src_frame(start, t - 1, L);
+  // pull every modality's current and previous rows towards L2 now: the per-modality phases below are dependent
+  // (reduce, then write), so without this each phase pays its own DRAM round trip
+#pragma unroll 1
+  for (int m = 0; m < p.M; ++m) {
+    const int bytes = p.raw_dim[m] * 4;
+    const char* c0 = reinterpret_cast<const char*>(p.src[m] + cur * p.raw_dim[m]);
+    const char* p0 = reinterpret_cast<const char*>(p.src[m] + prv * p.raw_dim[m]);
+    for (int o = lane * 128; o < bytes; o += 32 * 128) { prefetch_l2(c0 + o); prefetch_l2(p0 + o); }
+  }
   float* out = p.feats ? p.feats + gw * p.D : nullptr;
   __half* out16 = p.feats16 ? p.feats16 + gw * p.D16 : nullptr;
 
@@ -202,6 +224,11 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
 }
 
 }  // namespace
+
+cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* scale, float* shift, int D, cudaStream_t s) {
+  k_zscore_table<<<(D + 255) / 256, 256, 0, s>>>(mean, stdv, scale, shift, D);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
   if (p.n_windows <= 0) return cudaSuccess;

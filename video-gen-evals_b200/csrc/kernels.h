@@ -14,8 +14,8 @@ struct FuseParams {
   int raw_off16[TAG_MAX_MODALITIES], diff_off16[TAG_MAX_MODALITIES];   // padded fp16 operand columns
   const float* src[TAG_MAX_MODALITIES];
   const int64_t* frame_offset;
-  const float* mean;        // [D] or null
-  const float* stdv;        // [D] or null
+  const float* mean;        // [D] z-score SCALE table 1/(std+1e-6) (launch_zscore_table), or null
+  const float* stdv;        // [D] z-score SHIFT table -mean*scale, or null
   const int32_t* win_video;
   const int32_t* win_start;
   int64_t n_windows;
@@ -24,6 +24,7 @@ struct FuseParams {
   __half* feats16;          // [N,T,D16] or null (pad columns must be pre-zeroed by the caller)
   int32_t* flags;           // [1] or null
 };
+cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* scale, float* shift, int D, cudaStream_t s);
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s);
 
 // ------------------------------------------------------------------ K3 / K4 / N1 / N2

@@ -73,6 +73,8 @@ struct tag_handle {
   size_t prof_used = 0;
   double prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per kind: ms, flops, launches
   int* col_tab = nullptr;           // device [M][6] column map fp32 feats -> fp16 operand layout
+  float* zs_scale = nullptr;        // [D] z-score tables, rebuilt from (mean, std) at every feature-fuse call
+  float* zs_shift = nullptr;
 };
 
 namespace {
@@ -443,7 +445,9 @@ int fill_fuse_params(tag_handle* h, FuseParams* p, const tag_videos* vids, const
     if (p->kind[m] == TAG_KIND_PROCRUSTES) ++n_proc;
   }
   if (n_proc > 1) return fail(h, TAG_ERR_UNSUPPORTED, "at most one TAG_KIND_PROCRUSTES modality is supported");
-  p->frame_offset = vids->frame_offset; p->mean = mean; p->stdv = stdv;
+  p->frame_offset = vids->frame_offset;
+  p->mean = mean ? h->zs_scale : nullptr;      // the kernel reads the (scale, shift) tables
+  p->stdv = mean ? h->zs_shift : nullptr;
   p->win_video = win_video; p->win_start = win_start; p->n_windows = n; p->T = T; p->D = h->D; p->D16 = h->D16;
   return TAG_OK;
 }
@@ -499,6 +503,13 @@ int tag_create(tag_handle** out, const tag_config* cfg) {
   h->raw_total = off;
   for (int m = 0; m < h->M; ++m) { h->diff_off[m] = off; off += cfg->diff_dims[m]; h->diff_off16[m] = off16; off16 += round_up(cfg->diff_dims[m], 64); }
   h->D = off; h->D16 = off16;
+  if (cudaMalloc((void**)&h->zs_scale, (size_t)h->D * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&h->zs_shift, (size_t)h->D * sizeof(float)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, TAG_ERR_CUDA, "cudaMalloc of the z-score tables failed");
+  }
+  h->allocs.push_back(h->zs_scale);
+  h->allocs.push_back(h->zs_shift);
   *out = h;
   return TAG_OK;
 }
@@ -672,6 +683,7 @@ int tag_feature_fuse(tag_handle* h, const tag_videos* vids, const float* mean, c
   if (rc) return rc;
   p.feats = feats_out; p.feats16 = nullptr; p.flags = flags_out;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (mean) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
   LAUNCH_TRY(h, launch_feature_fuse(p, (cudaStream_t)stream));
   return TAG_OK;
 }
@@ -722,6 +734,7 @@ int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean,
   const bool tc = h->cfg.precision == TAG_PRECISION_FP16_TC;
   prof_begin(h);
   const int S = T + 1;
+  if (mean && stdv) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, s));
   for (int64_t w0 = 0; w0 < n_windows; w0 += h->cfg.max_windows) {
     const int64_t W = (n_windows - w0 < h->cfg.max_windows) ? n_windows - w0 : h->cfg.max_windows;
     FuseParams p;

@@ -121,11 +121,42 @@ class TagScorer:
         self.last_flags = enc["flags"]
         return ac, tc
 
-    def score_host(self, vb_host: VideoBatch, centroids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def score_host(self, vb_host: VideoBatch, centroids: torch.Tensor, pieces: int = 4) -> Tuple[torch.Tensor, torch.Tensor]:
         """End-to-end call with HOST buffers: H2D of every input array, score, D2H of the per-video
-        results. This is the `e2e` leg of bench.py. Returns CPU tensors (ac [V], tc [V])."""
-        dv = self.to_device(vb_host)
-        ac, tc = self.score(dv, centroids)
+        results. This is the `e2e` leg of bench.py. Returns CPU tensors (ac [V], tc [V]).
+
+        The batch is cut into `pieces` contiguous blocks of videos; block i+1 is copied on a side stream while
+        block i is being scored (the inputs are 350 KB per video, the results 8 B), so with pinned host memory the
+        PCIe time hides behind the encoder instead of adding to it."""
+        V = vb_host.n_videos
+        pieces = max(1, min(int(pieces), V))
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        cs.wait_stream(main)
+        ac = torch.empty(V, device=dev, dtype=torch.float32)
+        tc = torch.empty(V, device=dev, dtype=torch.float32)
+        bounds = [shard_range(V, i, pieces) for i in range(pieces)]
+        staged = []
+        for lo, hi in bounds:                      # enqueue all copies up front on the copy stream, in order
+            with torch.cuda.stream(cs):
+                piece = vb_host.slice(lo, hi).to(dev)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            staged.append((piece, ev))
+        flags = 0
+        for (lo, hi), (piece, ev) in zip(bounds, staged):
+            main.wait_event(ev)
+            for t in (piece.pose, piece.gori, piece.betas, piece.vit, piece.kp, piece.clip, piece.dino):
+                if t is not None:
+                    t.record_stream(main)
+            a, t_ = self.score(DeviceVideos(piece, self.model.modalities, dev), centroids)
+            ac[lo:hi].copy_(a)
+            tc[lo:hi].copy_(t_)
+            flags = self.last_flags if isinstance(flags, int) else flags + self.last_flags
+        self.last_flags = flags
         out = torch.stack([ac, tc], 0).cpu()
         return out[0], out[1]
 

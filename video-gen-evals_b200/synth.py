@@ -100,6 +100,14 @@ class VideoBatch:
                           [self.cls_idx[v] for v in vids], [self.names[v] for v in vids],
                           g(self.clip), g(self.dino), list(self.classes))
 
+    def slice(self, v0: int, v1: int) -> "VideoBatch":
+        """videos [v0, v1) as VIEWS of the packed arrays (no copy)."""
+        a, b = self.offsets[v0], self.offsets[v1]
+        g = lambda t: None if t is None else t[a:b]
+        return VideoBatch(g(self.pose), g(self.gori), g(self.betas), g(self.vit), g(self.kp),
+                          [o - a for o in self.offsets[v0:v1 + 1]], self.cls_idx[v0:v1], self.names[v0:v1],
+                          g(self.clip), g(self.dino), list(self.classes))
+
     def input_bytes(self) -> int:
         n = 0
         for t in (self.pose, self.gori, self.betas, self.vit, self.kp, self.clip, self.dino):
