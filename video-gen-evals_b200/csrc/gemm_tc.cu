@@ -35,7 +35,7 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;       // 16 KiB
 // CTA pairs (cta_group::2): each CTA stages its own 128 activation rows and HALF of the weight rows (16 KiB), the
 // pair's tcgen05.mma reads both halves -> 6 stages of 32 KiB and 1/3 less L2->SM traffic per FLOP.
 template <bool PAIR> struct Cfg {
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int STAGES = PAIR ? 5 : 3;
   static constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
@@ -47,9 +47,11 @@ constexpr int CW = 16;                        // columns per tcgen05.ld chunk
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int GN_RED_BYTES = 2 * EPI_WARPS * 32 * 8;     // double-buffered per-lane (sum, sumsq) exchange
-constexpr int RING_BYTES = 4 * (A_BYTES + BLOCK_N * BLOCK_K * 2);      // == 6 * 32 KiB
+constexpr int RING_BYTES = 5 * (A_BYTES + (BLOCK_N / 2) * BLOCK_K * 2);      // 5 x 32 KiB (pair) >= 3 x 48 KiB (single)
+constexpr int STG_WARP_BYTES = 32 * 64;            // per-epilogue-warp staging tile: 32 rows x 64 B, XOR-swizzled
+constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int GN_AFFINE_BYTES = 2 * BLOCK_N * 4;           // gamma[256] || beta[256]
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GN_RED_BYTES + GN_AFFINE_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GN_RED_BYTES + GN_AFFINE_BYTES + STG_BYTES;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> the pair's leader CTA
 
 // tcgen05 instruction descriptor (Cfg::IDESC), kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B,
@@ -72,6 +74,7 @@ struct TcParams {
   int act;
   const float* gn_gamma;   // GN instantiation only: GroupNorm(1 group) affine, fused after the activation
   const float* gn_beta;
+  int dbg;                 // bottleneck experiments (TAG_TC_DEBUG): 1 no epilogue stores, 2 no weight loads, 4 no activation loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -195,18 +198,54 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                :: "memory");
 }
 
-// fp16 residual of CW consecutive columns of one row, issued early so its L2 latency hides behind the accumulator wait
-__device__ __forceinline__ void load_res16(const TcParams& p, uint4 (&dst)[2], int64_t r, int n, bool row_ok) {
-  if (p.res16 != nullptr && row_ok) {
-    const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + r * (int64_t)p.ldr + n);
-    dst[0] = __ldg(rp); dst[1] = __ldg(rp + 1);
-  } else {
-    dst[0] = make_uint4(0u, 0u, 0u, 0u); dst[1] = dst[0];
+// ---- epilogue staging ------------------------------------------------------------------------------------------
+// TMEM hands a lane one ROW (32 lanes = 32 rows); written straight to global memory that is 16 B per lane at a
+// row-stride apart: 32 cache lines per warp instruction, and the LSU (one line per cycle) — not HBM — bounds the
+// kernel (micro-benchmark, profiles/r1_tc_microbench_bottleneck.log: the K = 256 GEMMs ran 2x faster with the stores
+// removed). So every epilogue global access goes through a per-warp shared-memory tile of 32 rows x 64 B: the
+// "row" view (lane = row, 16-byte chunk c) is what the TMEM math reads/writes, the "coalesced" view (instruction j:
+// row 8j + lane/4, chunk lane%4) is what global memory sees — 8 rows x 64 contiguous bytes per instruction.
+// 16-byte chunks are XOR-swizzled by ((row >> 1) & 3): both views are bank-conflict free.
+__device__ __forceinline__ uint32_t stg_addr(uint32_t base, int row, int chunk) {
+  return base + (uint32_t)(row * 64) + (uint32_t)(((chunk ^ (row >> 1)) & 3) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+// coalesced global -> registers of one 32-row x 64-byte unit (rows row0.., byte offset `off` in each row of pitch
+// `pitch` bytes); rows >= M read as zero
+__device__ __forceinline__ void unit_load(const char* base, int64_t pitch, int64_t row0, int64_t M, int64_t off, int lane, uint4 (&r)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t row = row0 + 8 * j + (lane >> 2);
+    r[j] = (base != nullptr && row < M) ? __ldg(reinterpret_cast<const uint4*>(base + row * pitch + off + (lane & 3) * 16))
+                                        : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void unit_to_smem(uint32_t stg, int lane, const uint4 (&r)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sts128(stg_addr(stg, 8 * j + (lane >> 2), lane & 3), r[j]);
+}
+// staging tile -> global, coalesced
+__device__ __forceinline__ void unit_store(char* base, int64_t pitch, int64_t row0, int64_t M, int64_t off, int lane, uint32_t stg) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t row = row0 + 8 * j + (lane >> 2);
+    const uint4 v = lds128(stg_addr(stg, 8 * j + (lane >> 2), lane & 3));
+    if (row < M) *reinterpret_cast<uint4*>(base + row * pitch + off + (lane & 3) * 16) = v;
   }
 }
 
-// v = act(acc + bias + res) for CW consecutive columns of one row
-__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[CW], const uint4 (&res)[2], float (&v)[CW], int64_t r, int n) {
+// v = act(acc + bias + res) for CW consecutive columns of one row; the residual comes from the staging tile
+// (RES = 0 none, 16: two 16-byte chunks of fp16, 32: four 16-byte chunks of fp32)
+template <int RES>
+__device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[CW], uint32_t stg, int lane, int chunk0,
+                                           float (&v)[CW], int n) {
 #pragma unroll
   for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
   if (p.bias != nullptr) {
@@ -216,20 +255,21 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
       v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
   }
-  if (p.res16 != nullptr) {
+  if constexpr (RES == 16) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const __half2* hh = reinterpret_cast<const __half2*>(&res[i]);
+      const uint4 u = lds128(stg_addr(stg, lane, chunk0 + i));
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
     }
   }
-  if (p.res32 != nullptr) {
-    const float4* rp = reinterpret_cast<const float4*>(p.res32 + r * (int64_t)p.N + n);
+  if constexpr (RES == 32) {
 #pragma unroll
-    for (int i = 0; i < CW / 4; ++i) {
-      const float4 f = __ldg(rp + i);
-      v[i * 4] += f.x; v[i * 4 + 1] += f.y; v[i * 4 + 2] += f.z; v[i * 4 + 3] += f.w;
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = lds128(stg_addr(stg, lane, i));
+      v[i * 4] += __uint_as_float(u.x); v[i * 4 + 1] += __uint_as_float(u.y);
+      v[i * 4 + 2] += __uint_as_float(u.z); v[i * 4 + 3] += __uint_as_float(u.w);
     }
   }
   if (p.act == 1) {
@@ -319,14 +359,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const int shift = (p.taps > 1) ? (j - p.taps / 2) * p.dil : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const bool ld_a = !(p.dbg & 4), ld_b = !(p.dbg & 2);
+          const uint32_t tx = (ld_a ? A_BYTES : 0) + (ld_b ? Cfg<PAIR>::B_BYTES : 0);
           if constexpr (PAIR) {
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);       // bytes of both CTAs
-            tma_load_3d_pair(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
-            tma_load_2d_pair(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            if (leader) { if (tx) mbar_arrive_expect_tx(full_bar(stage), 2 * tx); else mbar_arrive(full_bar(stage)); }   // bytes of both CTAs
+            if (ld_a) tma_load_3d_pair(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+            if (ld_b) tma_load_2d_pair(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
           } else {
-            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
-            tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
+            if (tx) mbar_arrive_expect_tx(full_bar(stage), tx); else mbar_arrive(full_bar(stage));
+            if (ld_a) tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+            if (ld_b) tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -368,46 +410,51 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;          // which 64 accumulator columns
     constexpr int NCH = EPI_COLS / CW;         // 4 chunks of 16 columns
+    const uint32_t stg = bar_base + 256u + GN_RED_BYTES + GN_AFFINE_BYTES + (uint32_t)((warp - 2) * STG_WARP_BYTES);
+    const bool out32 = p.C32 != nullptr;
     int64_t it = 0;
     for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int64_t m_tile = m_tile_of(tile);
       const int n_tile = (int)(tile % p.n_tiles);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int64_t r = m_tile * BLOCK_M + q * 32 + lane;
-      const bool row_ok = r < p.M;
+      const int64_t row0 = m_tile * BLOCK_M + q * 32;          // first row of this warp
       const int n_base = n_tile * BLOCK_N + part * EPI_COLS;
-      uint4 res_cur[2];
-      load_res16(p, res_cur, r, n_base, row_ok);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + part * EPI_COLS);
       if constexpr (GN) {
         // ---- pass 1: z = GELU(acc + res), per-row partial sums, z stashed as fp16 pairs in registers
         uint32_t stash[EPI_COLS / 2];
         float s1 = 0.f, s2 = 0.f;
+        uint4 rres[4];
+        unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)n_base * 2, lane, rres);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t raw[CW];
-          tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
-          uint4 res_next[2];
-          if (c + 1 < NCH) load_res16(p, res_next, r, n_base + (c + 1) * CW, row_ok);
-          tmem_ld16_wait(raw);
-          float v[CW];
-          if (row_ok) {
-            epi_values(p, raw, res_cur, v, r, n_base + c * CW);
-          } else {
+        for (int u = 0; u < 2; ++u) {                           // units of 32 fp16 columns
+          unit_to_smem(stg, lane, rres);
+          __syncwarp();
+          if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
 #pragma unroll
-            for (int i = 0; i < CW; ++i) v[i] = 0.f;
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = u * 2 + cc;
+            uint32_t raw[CW];
+            tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
+            tmem_ld16_wait(raw);
+            float v[CW];
+            epi_values<16>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+            if (row0 + lane >= p.M) {
+#pragma unroll
+              for (int i = 0; i < CW; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+#pragma unroll
+            for (int i = 0; i < CW / 2; ++i) {
+              const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+              stash[c * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
           }
-#pragma unroll
-          for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
-#pragma unroll
-          for (int i = 0; i < CW / 2; ++i) {
-            const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-            stash[c * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&h2);
-          }
-          if (c + 1 < NCH) { res_cur[0] = res_next[0]; res_cur[1] = res_next[1]; }
+          __syncwarp();                                         // everyone has read its residual rows of this unit
         }
         // the accumulator has been read completely: hand the TMEM buffer back to the MMA warp now
         tc_fence_before();
@@ -438,63 +485,107 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const float var = fmaxf(S2 * inv_n - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
-        // ---- pass 2: normalise the stash, per-channel affine (from shared memory), store fp16
-        if (row_ok) {
-          const int nl = part * EPI_COLS;
-          uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + nl);
+        // ---- pass 2: normalise the stash, per-channel affine (from shared memory), stage, store coalesced
+        const int nl = part * EPI_COLS;
 #pragma unroll
-          for (int i = 0; i < EPI_COLS / 8; ++i) {
-            uint4 u;
-            __half2* hh = reinterpret_cast<__half2*>(&u);
-            const float4 g0 = *reinterpret_cast<const float4*>(s_gb + nl + i * 8);
-            const float4 g1 = *reinterpret_cast<const float4*>(s_gb + nl + i * 8 + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + nl + i * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + nl + i * 8 + 4);
+        for (int u = 0; u < 2; ++u) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {                         // 4 chunks of 8 columns
+            const int col = nl + u * 32 + i * 8;
+            uint4 o;
+            __half2* hh = reinterpret_cast<__half2*>(&o);
+            const float4 g0 = *reinterpret_cast<const float4*>(s_gb + col);
+            const float4 g1 = *reinterpret_cast<const float4*>(s_gb + col + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + col);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + col + 4);
             const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&stash[i * 4 + e]));
+              const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&stash[u * 16 + i * 4 + e]));
               hh[e] = __floats2half2_rn(fmaf(fmaf(z.x, rstd, nmr), gg[2 * e], bb[2 * e]),
                                         fmaf(fmaf(z.y, rstd, nmr), gg[2 * e + 1], bb[2 * e + 1]));
             }
-            op[i] = u;
+            sts128(stg_addr(stg, lane, i), o);
           }
+          __syncwarp();
+          unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(nl + u * 32) * 2, lane, stg);
+          __syncwarp();
+        }
+      } else if (!out32) {
+        // ---- fp16 output (optional fp16 residual): 2 units of 32 columns
+        const bool has_res = p.res16 != nullptr;
+        uint4 rres[4];
+        if (has_res) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)n_base * 2, lane, rres);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (has_res) {
+            unit_to_smem(stg, lane, rres);
+            __syncwarp();
+            if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = u * 2 + cc;
+            uint32_t raw[CW];
+            tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
+            tmem_ld16_wait(raw);
+            float v[CW];
+            if (has_res) epi_values<16>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+            else epi_values<0>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 o;
+              __half2* hh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
+              sts128(stg_addr(stg, lane, cc * 2 + i), o);       // over this lane's own (already consumed) residual chunk
+            }
+          }
+          if (u == 1) {                                         // last TMEM read done: release the accumulator early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+          }
+          __syncwarp();
+          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(n_base + u * 32) * 2, lane, stg);
+          __syncwarp();
         }
       } else {
+        // ---- fp32 output (optional fp32 residual, ld = N): 4 units of 16 columns
+        const bool has_res = p.res32 != nullptr;
+        uint4 rres[4];
+        if (has_res) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)n_base * 4, lane, rres);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          uint32_t raw[CW];
-          tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
-          uint4 res_next[2];
-          if (c + 1 < NCH) load_res16(p, res_next, r, n_base + (c + 1) * CW, row_ok);
-          tmem_ld16_wait(raw);
-          if (row_ok) {
-            const int n = n_base + c * CW;
-            float v[CW];
-            epi_values(p, raw, res_cur, v, r, n);
-            if (p.C16 != nullptr) {
-              uint4* op = reinterpret_cast<uint4*>(p.C16 + r * (int64_t)p.ldc + n);
-#pragma unroll
-              for (int i = 0; i < CW / 8; ++i) {
-                uint4 u;
-                __half2* hh = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(v[i * 8 + 2 * e], v[i * 8 + 2 * e + 1]);
-                op[i] = u;
-              }
-            }
-            if (p.C32 != nullptr) {
-              float4* op = reinterpret_cast<float4*>(p.C32 + r * (int64_t)p.N + n);
-#pragma unroll
-              for (int i = 0; i < CW / 4; ++i) op[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-            }
+        for (int u = 0; u < NCH; ++u) {
+          if (has_res) {
+            unit_to_smem(stg, lane, rres);
+            __syncwarp();
+            if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + (u + 1) * CW) * 4, lane, rres);
           }
-          if (c + 1 < NCH) { res_cur[0] = res_next[0]; res_cur[1] = res_next[1]; }
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+          float v[CW];
+          if (has_res) epi_values<32>(p, raw, stg, lane, 0, v, n_base + u * CW);
+          else epi_values<0>(p, raw, stg, lane, 0, v, n_base + u * CW);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(stg_addr(stg, lane, i), make_uint4(__float_as_uint(v[i * 4]), __float_as_uint(v[i * 4 + 1]),
+                                                      __float_as_uint(v[i * 4 + 2]), __float_as_uint(v[i * 4 + 3])));
+          if (u == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+          }
+          __syncwarp();
+          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + u * CW) * 4, lane, stg);
+          __syncwarp();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
       }
     }
   }
@@ -519,6 +610,7 @@ struct TcContext {
   EncodeTiledFn encode = nullptr;
   int num_sms = 148;
   bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
+  int dbg = 0;            // TAG_TC_DEBUG bottleneck experiments (results are wrong when set)
 };
 
 TcContext* tc_context_create(int device, char* err, int errlen) {
@@ -540,6 +632,8 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const char* env = getenv("TAG_TC_PAIR");
   if (env != nullptr) c->pair = env[0] != '0';
+  env = getenv("TAG_TC_DEBUG");
+  if (env != nullptr) c->dbg = atoi(env);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
     delete c;
@@ -562,7 +656,12 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   if (g.lda % 8 || (reinterpret_cast<uintptr_t>(g.A) & 15)) return bad("A must be 16-byte aligned with lda % 8 == 0");
   if (reinterpret_cast<uintptr_t>(g.W) & 15) return bad("W must be 16-byte aligned");
   if (g.A2 != nullptr) return bad("second K segment not built yet");
-  if (g.C16 == nullptr && g.C32 == nullptr) return bad("no output");
+  if ((g.C16 == nullptr) == (g.C32 == nullptr)) return bad("exactly one of C16 / C32 must be given");
+  if (g.C32 != nullptr && g.res16 != nullptr) return bad("fp32 output takes an fp32 residual");
+  if (g.C16 != nullptr && g.res32 != nullptr) return bad("fp16 output takes an fp16 residual");
+  if (g.res16 != nullptr && g.res32 != nullptr) return bad("one residual at most");
+  if (g.res32 && (reinterpret_cast<uintptr_t>(g.res32) & 15)) return bad("res32 alignment");
+  if (g.C32 && (reinterpret_cast<uintptr_t>(g.C32) & 15)) return bad("C32 alignment");
   if (g.C16 && ((g.ldc % 8) || (reinterpret_cast<uintptr_t>(g.C16) & 15))) return bad("C16 alignment");
   if (g.res16 && ((g.ldr % 8) || (reinterpret_cast<uintptr_t>(g.res16) & 15))) return bad("res16 alignment");
 
@@ -570,6 +669,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   p.M = g.M; p.N = g.N; p.kb_per_tap = g.K / BLOCK_K; p.taps = g.taps; p.dil = g.dil; p.T = g.T;
   p.bias = g.bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
   p.gn_gamma = g.gn_gamma; p.gn_beta = g.gn_beta;
+  p.dbg = ctx->dbg;
   const bool gn = g.gn_gamma != nullptr;
   if (gn) {
     if (g.gn_beta == nullptr || g.taps <= 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 != nullptr || g.T > BLOCK_M ||
