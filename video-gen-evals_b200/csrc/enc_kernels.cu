@@ -69,6 +69,37 @@ __device__ __forceinline__ void row_norm(float (&v)[8]) {
 }
 
 // ---------------------------------------------------------------- A11 + A12 (front half)
+// s = state + motion -> F.layer_norm (no affine, model.py:175) -> fusion.kv_ln (affine, model.py:81) -> logit ->
+// softmax over modalities -> sum_m A_m kv_m. The second LayerNorm needs no reductions of its own: its input
+// u = (s - mean) * rstd1 has mean 0 and variance v / (v + eps) (v = var(s)), so
+// kv = (s - mean) * rstd1 * rstd2 * gamma + beta with rstd2 = 1 / sqrt(v / (v + eps) + eps).
+// (The reference evaluates mean(u) numerically; it is 0 up to fp32 round-off, ~1e-8.)
+// kv_m is held as packed fp16 pairs between the logit pass and the mixing pass when activations are fp16 (the mix is
+// stored as fp16 anyway), which keeps the kernel at 3+ CTAs per SM.
+template <typename TA> struct KvHold;
+template <> struct KvHold<float> {
+  float v[8];
+  __device__ __forceinline__ void put(const float (&x)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = x[k];
+  }
+  __device__ __forceinline__ void get(float (&x)[8]) const {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = v[k];
+  }
+};
+template <> struct KvHold<__half> {
+  __half2 v[4];
+  __device__ __forceinline__ void put(const float (&x)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+  }
+  __device__ __forceinline__ void get(float (&x)[8]) const {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(v[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+  }
+};
+
 template <typename TA>
 __global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
   const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -78,7 +109,7 @@ __global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
   Row8<float>::load(p.kv_gamma + lane * 8, g);
   Row8<float>::load(p.kv_beta + lane * 8, b);
   Row8<float>::load(p.qk + lane * 8, qk);
-  float kv[TAG_MAX_MODALITIES][8];
+  KvHold<TA> kv[TAG_MAX_MODALITIES];
   float logit[TAG_MAX_MODALITIES];
   float mx = -CUDART_INF_F;
 #pragma unroll
@@ -92,11 +123,21 @@ __global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] += u[k];             // s = state + motion  (model.py:174)
       }
-      row_norm(v);                                            // F.layer_norm, no affine (model.py:175)
-      row_norm(v);                                            // fusion.kv_ln (model.py:81) ...
+      float sm = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sm += v[k];
+      const float mean = warp_sum(sm) * (1.0f / kD);
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { v[k] -= mean; sq = fmaf(v[k], v[k], sq); }
+      const float var = warp_sum(sq) * (1.0f / kD);
+      const float rstd1 = 1.0f / sqrtf(var + kLnEps);
+      const float var_u = var * rstd1 * rstd1;                // variance of the first LayerNorm's output
+      const float sc = rstd1 / sqrtf(var_u + kLnEps);
       float d = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { v[k] = v[k] * g[k] + b[k]; kv[m][k] = v[k]; d += v[k] * qk[k]; }
+      for (int k = 0; k < 8; ++k) { v[k] = fmaf(v[k] * sc, g[k], b[k]); d = fmaf(v[k], qk[k], d); }
+      kv[m].put(v);
       d = warp_sum(d);                                        // Q . (Wk kv) / sqrt(D)
       logit[m] = d * p.inv_tau[m] + p.lbias[m];               // model.py:89-91
       mx = fmaxf(mx, logit[m]);
@@ -106,15 +147,18 @@ __global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
 #pragma unroll
   for (int m = 0; m < TAG_MAX_MODALITIES; ++m)
     if (m < p.M) { logit[m] = expf(logit[m] - mx); den += logit[m]; }
+  const float inv_den = 1.0f / den;
   float mix[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) mix[k] = 0.f;
 #pragma unroll
   for (int m = 0; m < TAG_MAX_MODALITIES; ++m)
     if (m < p.M) {
-      const float a = logit[m] / den;
+      const float a = logit[m] * inv_den;
+      float x[8];
+      kv[m].get(x);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mix[k] += a * kv[m][k];
+      for (int k = 0; k < 8; ++k) mix[k] = fmaf(a, x[k], mix[k]);
       if (p.attn != nullptr && lane == 0) p.attn[r * p.M + m] = a;
     }
   Row8<TA>::store(reinterpret_cast<TA*>(p.mix) + r * kD + lane * 8, mix);

@@ -148,10 +148,13 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
               E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
           float tr = E[0] + E[4] + E[8];
           tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
-          const float theta = acosf((tr - 1.f) / 2.f);
-          const float den = fmaxf(2.f * sinf(theta), 1e-6f);
-          const float v0 = (E[7] - E[5]) / den, v1 = (E[2] - E[6]) / den, v2 = (E[3] - E[1]) / den;
-          const float wv[3] = {theta * v0, theta * v1, theta * v2};
+          const float c = (tr - 1.f) / 2.f;
+          const float theta = acosf(c);
+          // 2 sin(theta) with theta in [0, pi]: sin = sqrt((1-c)(1+c)); 1-c is exact in fp32 near c = 1, so this is
+          // at least as accurate as sinf(acosf(c)) and costs one sqrt instead of a libm sine
+          const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
+          const float k = theta / den;
+          const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const float d = nz(wv[k], dofs + jn * 3 + k);
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
           const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
           x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
           x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
-          const float sc = fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
-          x0 /= sc; y0 /= sc; x1 /= sc; y1 /= sc;
+          const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
+          x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
         };
         float x0, y0, x1, y1, px0, py0, px1, py1;
         load_norm(xc, x0, y0, x1, y1);
@@ -201,9 +204,11 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
           const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
           const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
           if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
-          const float ang = atan2f(h10 - h01, h00 + h11);
-          float sn, cs;
-          sincosf(ang, &sn, &cs);
+          // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
+          const float ry = h10 - h01, rx = h00 + h11;
+          const float rr = ry * ry + rx * rx;
+          const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
+          const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
           // X @ R with R = [[c, s], [-s, c]]  (== Vh @ U.T for det(H) > 0)
           d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
           d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
