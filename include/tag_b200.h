@@ -157,13 +157,16 @@ int tag_get_profile(tag_handle* h, double* out9);
 /* --- test hooks: the two GEMM kernels in isolation (tests/test_gemm_gpu.py).
  *     C = act(sum_taps A[row+shift] W^T + bias + res); fp32: W [N, ldw]; tensor-core: A/W/res16/C16
  *     are fp16, W [N, taps*K], ld of res/C = N; gn_gamma/gn_beta non-NULL fuse GroupNorm(1,256) over each
- *     (T x 256) window after the activation (conv only, N == 256, T a power of two <= 128). */
+ *     (T x 256) window after the activation (conv only, N == 256, T a power of two <= 128); ln_gamma/ln_beta
+ *     non-NULL fuse LayerNorm over the 256 output columns after bias + fp32 residual (plain GEMM, N == 256; writes
+ *     C32, which may alias res32, and its fp16 copy C16). */
 int tag_debug_gemm_f32(tag_handle* h, const float* A, int32_t lda, const float* W, int32_t ldw, int64_t M, int32_t N,
                        int32_t K, int32_t taps, int32_t dil, int32_t T, const float* bias, const float* res, float* C,
                        int32_t act, void* stream);
 int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, int64_t M, int32_t N, int32_t K,
                       int32_t taps, int32_t dil, int32_t T, const float* bias, const void* res16, const float* res32,
-                      void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta, void* stream);
+                      void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta,
+                      const float* ln_gamma, const float* ln_beta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ def _run_tc(M, N, K, taps, dil, T, act, use_bias, res_kind, out_kind, seed=0):
     C16 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16) if out_kind in (16, 48) else None
     C32 = torch.full((M, N), float("nan"), device=DEV) if out_kind in (32, 48) else None
     rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, W.data_ptr(), M, N, K, taps, dil, T, _lib.ptr(bias), _lib.ptr(res16),
-                               _lib.ptr(res32), _lib.ptr(C16), _lib.ptr(C32), act, None, None,
+                               _lib.ptr(res32), _lib.ptr(C16), _lib.ptr(C32), act, None, None, None, None,
                                torch.cuda.current_stream().cuda_stream)
     _lib.check(h, rc, "tag_debug_gemm_tc")
     torch.cuda.synchronize()
@@ -100,15 +100,15 @@ def test_gemm_tc_rejects_unsupported_shapes():
     Cc = torch.zeros(96, 256, device=DEV, dtype=torch.float16)
     s = torch.cuda.current_stream().cuda_stream
     # T = 48 neither divides 128 nor is a multiple of it
-    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 5, 1, 48, None, None, None, Cc.data_ptr(), None, 0, None, None, s) != 0
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 5, 1, 48, None, None, None, Cc.data_ptr(), None, 0, None, None, None, None, s) != 0
     assert b"T dividing 128" in lib.tag_last_error(h)
-    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 100, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 0, None, None, s) != 0
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 100, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 0, None, None, None, None, s) != 0
     # exactly one output
     C32 = torch.zeros(96, 256, device=DEV)
-    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), C32.data_ptr(), 0, None, None, s) != 0
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), C32.data_ptr(), 0, None, None, None, None, s) != 0
     # fused GroupNorm only for convs whose tile owns whole windows
     g = torch.ones(256, device=DEV)
-    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 1, g.data_ptr(), g.data_ptr(), s) != 0
+    assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 1, g.data_ptr(), g.data_ptr(), None, None, s) != 0
 
 
 @pytest.mark.parametrize("W_,T,dil", [(8, 32, 1), (37, 32, 8), (12, 16, 2), (5, 64, 4), (3, 128, 8), (150 * 4, 32, 2), (9, 8, 1)])
@@ -130,7 +130,7 @@ def test_gemm_tc_fused_groupnorm(W_, T, dil):
     ref = ref * gamma.double() + beta.double()
     buf = res.clone()                                                                       # in place: C16 == res16
     rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, Wt.data_ptr(), M, N, K, taps, dil, T, None, buf.data_ptr(), None,
-                               buf.data_ptr(), None, 1, gamma.data_ptr(), beta.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                               buf.data_ptr(), None, 1, gamma.data_ptr(), beta.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)
     _lib.check(h, rc, "tag_debug_gemm_tc(gn)")
     torch.cuda.synchronize()
     err = (buf.double() - ref).abs().max().item()
@@ -175,3 +175,30 @@ def test_fused_pipeline_tc_scores():
     print(f"fused tc pipeline: AC rel {e_ac:.2e} TC rel {e_tc:.2e}")
     assert e_ac < 1e-3 and e_tc < 1e-3
     assert int(scorer.last_flags.item()) == 0
+
+
+@pytest.mark.parametrize("M,K", [(330, 256), (128 * 9 + 5, 1024), (64, 256)])
+def test_gemm_tc_fused_layernorm(M, K):
+    """out-proj / FFN2 form of the post-norm transformer layer (model.py:145): X <- LayerNorm(A W^T + b + X), fp32 stream
+    updated in place plus its fp16 copy."""
+    lib = _lib.load()
+    h = tb.scoring.util_handle(DEV)
+    N = 256
+    gen = torch.Generator(device=DEV).manual_seed(M + K)
+    A = torch.randn(M, K, device=DEV, generator=gen).half()
+    Wt = (torch.randn(N, K, device=DEV, generator=gen) / math.sqrt(K)).half()
+    bias = 0.1 * torch.randn(N, device=DEV, generator=gen)
+    X = torch.randn(M, N, device=DEV, generator=gen)
+    gamma = 1.0 + 0.1 * torch.randn(N, device=DEV, generator=gen)
+    beta = 0.05 * torch.randn(N, device=DEV, generator=gen)
+    v = A.double() @ Wt.double().T + bias.double() + X.double()
+    ref = (v - v.mean(1, keepdim=True)) / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-5) * gamma.double() + beta.double()
+    X16 = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float16)
+    rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, Wt.data_ptr(), M, N, K, 1, 1, 1, bias.data_ptr(), None, X.data_ptr(),
+                               X16.data_ptr(), X.data_ptr(), 0, None, None, gamma.data_ptr(), beta.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+    _lib.check(h, rc, "tag_debug_gemm_tc(ln)")
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    assert (X.double() - ref).abs().max().item() < 2e-4 * scale, _diag(X, ref, "LN fp32")
+    assert (X16.double() - ref).abs().max().item() < 2e-3 * scale, _diag(X16, ref, "LN fp16")

@@ -24,7 +24,7 @@ def bench(name, M, N, K, taps, dil, T, act, res, gn, out32=False, reps=20):
     bet = torch.zeros(N, device=DEV) if gn else None
     def run():
         rc = lib.tag_debug_gemm_tc(h, A.data_ptr(), K, W.data_ptr(), M, N, K, taps, dil, T, None, _lib.ptr(R16), _lib.ptr(R32),
-                                   _lib.ptr(C16), _lib.ptr(C32), act, _lib.ptr(gam), _lib.ptr(bet), s)
+                                   _lib.ptr(C16), _lib.ptr(C32), act, _lib.ptr(gam), _lib.ptr(bet), None, None, s)
         _lib.check(h, rc, name)
     for _ in range(3):
         run()

@@ -74,6 +74,8 @@ struct TcParams {
   int act;
   const float* gn_gamma;   // GN instantiation only: GroupNorm(1 group) affine, fused after the activation
   const float* gn_beta;
+  const float* ln_gamma;   // MODE 2 only: LayerNorm over the 256 output columns (N == 256), fused after bias + residual;
+  const float* ln_beta;    //   writes the fp32 stream (C32, may alias res32) and its fp16 copy (C16)
   int dbg;                 // bottleneck experiments (TAG_TC_DEBUG): 1 no epilogue stores, 2 no weight loads, 4 no activation loads
 };
 
@@ -198,6 +200,16 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16]) {
                :: "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- epilogue staging ------------------------------------------------------------------------------------------
 // TMEM hands a lane one ROW (32 lanes = 32 rows); written straight to global memory that is 16 B per lane at a
 // row-stride apart: 32 cache lines per warp instruction, and the LSU (one line per cycle) — not HBM — bounds the
@@ -291,7 +303,11 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
 // its half of the weight rows; all TMA bytes are counted on the leader CTA's full barrier; the leader's elected thread
 // issues the MMAs and its commits are multicast to the empty / accumulator-full barriers of both CTAs; the peer's
 // epilogue warps release accumulators on the leader's barrier.
-template <bool GN, bool PAIR>
+// MODE: 0 plain epilogue, 1 fused GroupNorm (GN), 2 fused LayerNorm (LN): out-proj / FFN2 of the transformer layer
+// (post-norm, reference model.py:145): y = LN(acc + bias + x) * gamma + beta, x the fp32 token stream. The pre-norm sum
+// is parked in the accumulator's own TMEM columns (tcgen05.st) between the statistics pass and the normalise pass, so
+// neither registers nor shared memory have to hold the 128 x 256 fp32 tile.
+template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int STAGES = Cfg<PAIR>::STAGES;
@@ -301,6 +317,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const uint32_t bar_base = smem_base + RING_BYTES;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
+  constexpr bool GN = MODE == 1;
+  constexpr bool LN = MODE == 2;
   // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -312,6 +330,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   float* s_gb = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + GN_RED_BYTES);
   if constexpr (GN) {
     for (int i = threadIdx.x; i < BLOCK_N; i += THREADS) { s_gb[i] = __ldg(p.gn_gamma + i); s_gb[BLOCK_N + i] = __ldg(p.gn_beta + i); }
+  }
+  if constexpr (LN) {
+    for (int i = threadIdx.x; i < BLOCK_N; i += THREADS) { s_gb[i] = __ldg(p.ln_gamma + i); s_gb[BLOCK_N + i] = __ldg(p.ln_beta + i); }
   }
 
   if (threadIdx.x == 0) {
@@ -512,6 +533,88 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(nl + u * 32) * 2, lane, stg);
           __syncwarp();
         }
+      } else if constexpr (LN) {
+        // ---- pass 1: v = acc + bias + x (fp32 residual, staged coalesced), row sums, v parked back into TMEM
+        float s1 = 0.f, s2 = 0.f;
+        uint4 rres[4];
+        unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)n_base * 4, lane, rres);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          unit_to_smem(stg, lane, rres);
+          __syncwarp();
+          if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + (u + 1) * CW) * 4, lane, rres);
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+          float v[CW];
+          epi_values<32>(p, raw, stg, lane, 0, v, n_base + u * CW);
+#pragma unroll
+          for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); raw[i] = __float_as_uint(v[i]); }
+          tmem_st16(t_row + (uint32_t)(u * CW), raw);
+          __syncwarp();                                         // residual unit consumed before the next one is staged
+        }
+        tmem_st_wait();
+        // ---- row statistics across the 4 column parts of this lane quarter
+        const uint32_t red = bar_base + 256u + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
+        float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < EPI_WARPS / 4; ++pp) {
+          const int e = pp * 4 + ((q - 2) & 3);
+          float a, b;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)((e * 32 + lane) * 8)) : "memory");
+          S1 += a; S2 += b;
+        }
+        const float mean = S1 * (1.0f / BLOCK_N);
+        const float var = fmaxf(S2 * (1.0f / BLOCK_N) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float nmr = -mean * rstd;
+        // ---- pass 2: normalise, affine; fp32 stream (16 columns per unit) and fp16 copy (32 columns per two units)
+        const int nl = part * EPI_COLS;
+        uint32_t h16[CW];                                       // fp16 pairs of two consecutive units
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+          if (u == NCH - 1) {                                   // last TMEM read: release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+          }
+          float y[CW];
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(s_gb + nl + u * CW + i);
+            const float4 b = *reinterpret_cast<const float4*>(s_gb + BLOCK_N + nl + u * CW + i);
+            y[i] = fmaf(fmaf(__uint_as_float(raw[i]), rstd, nmr), g.x, b.x);
+            y[i + 1] = fmaf(fmaf(__uint_as_float(raw[i + 1]), rstd, nmr), g.y, b.y);
+            y[i + 2] = fmaf(fmaf(__uint_as_float(raw[i + 2]), rstd, nmr), g.z, b.z);
+            y[i + 3] = fmaf(fmaf(__uint_as_float(raw[i + 3]), rstd, nmr), g.w, b.w);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(stg_addr(stg, lane, i), make_uint4(__float_as_uint(y[i * 4]), __float_as_uint(y[i * 4 + 1]),
+                                                      __float_as_uint(y[i * 4 + 2]), __float_as_uint(y[i * 4 + 3])));
+#pragma unroll
+          for (int i = 0; i < CW / 2; ++i) {
+            const __half2 t = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+            h16[(u & 1) * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          __syncwarp();
+          unit_store(reinterpret_cast<char*>(p.C32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + u * CW) * 4, lane, stg);
+          __syncwarp();
+          if (u & 1) {                                          // two units done: 32 fp16 columns = one 64-byte unit
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sts128(stg_addr(stg, lane, i), make_uint4(h16[i * 4], h16[i * 4 + 1], h16[i * 4 + 2], h16[i * 4 + 3]));
+            __syncwarp();
+            unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(n_base + (u - 1) * CW) * 2, lane, stg);
+            __syncwarp();
+          }
+        }
       } else if (!out32) {
         // ---- fp16 output (optional fp16 residual): 2 units of 32 columns
         const bool has_res = p.res16 != nullptr;
@@ -626,10 +729,12 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-  e = cudaFuncSetAttribute(k_gemm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(k_gemm_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const char* env = getenv("TAG_TC_PAIR");
   if (env != nullptr) c->pair = env[0] != '0';
   env = getenv("TAG_TC_DEBUG");
@@ -656,9 +761,16 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   if (g.lda % 8 || (reinterpret_cast<uintptr_t>(g.A) & 15)) return bad("A must be 16-byte aligned with lda % 8 == 0");
   if (reinterpret_cast<uintptr_t>(g.W) & 15) return bad("W must be 16-byte aligned");
   if (g.A2 != nullptr) return bad("second K segment not built yet");
-  if ((g.C16 == nullptr) == (g.C32 == nullptr)) return bad("exactly one of C16 / C32 must be given");
-  if (g.C32 != nullptr && g.res16 != nullptr) return bad("fp32 output takes an fp32 residual");
-  if (g.C16 != nullptr && g.res32 != nullptr) return bad("fp16 output takes an fp16 residual");
+  const bool ln = g.ln_gamma != nullptr;
+  if (ln) {
+    if (g.ln_beta == nullptr || g.taps != 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 == nullptr || g.res32 == nullptr ||
+        g.res16 != nullptr || g.gn_gamma != nullptr || g.act != 0)
+      return bad("fused LayerNorm needs a plain GEMM with N == 256, an fp32 residual and both outputs");
+  } else {
+    if ((g.C16 == nullptr) == (g.C32 == nullptr)) return bad("exactly one of C16 / C32 must be given");
+    if (g.C32 != nullptr && g.res16 != nullptr) return bad("fp32 output takes an fp32 residual");
+    if (g.C16 != nullptr && g.res32 != nullptr) return bad("fp16 output takes an fp16 residual");
+  }
   if (g.res16 != nullptr && g.res32 != nullptr) return bad("one residual at most");
   if (g.res32 && (reinterpret_cast<uintptr_t>(g.res32) & 15)) return bad("res32 alignment");
   if (g.C32 && (reinterpret_cast<uintptr_t>(g.C32) & 15)) return bad("C32 alignment");
@@ -669,6 +781,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   p.M = g.M; p.N = g.N; p.kb_per_tap = g.K / BLOCK_K; p.taps = g.taps; p.dil = g.dil; p.T = g.T;
   p.bias = g.bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
   p.gn_gamma = g.gn_gamma; p.gn_beta = g.gn_beta;
+  p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta;
   p.dbg = ctx->dbg;
   const bool gn = g.gn_gamma != nullptr;
   if (gn) {
@@ -729,12 +842,14 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<true, true>, map_a, map_b, p);
-    return cudaLaunchKernelEx(&cfg, k_gemm_tc<false, true>, map_a, map_b, p);
+    if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<1, true>, map_a, map_b, p);
+    if (ln) return cudaLaunchKernelEx(&cfg, k_gemm_tc<2, true>, map_a, map_b, p);
+    return cudaLaunchKernelEx(&cfg, k_gemm_tc<0, true>, map_a, map_b, p);
   }
   const int64_t total = p.m_tiles * p.n_tiles;
   const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
-  if (gn) k_gemm_tc<true, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
-  else k_gemm_tc<false, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  if (gn) k_gemm_tc<1, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  else if (ln) k_gemm_tc<2, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  else k_gemm_tc<0, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
   return cudaGetLastError();
 }

@@ -57,7 +57,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // warp shuffle, so there is no block barrier and no shared memory; the previous frame's quantities are recomputed
 // from its row (an L1/L2 hit: the neighbouring warp of the same CTA streams that row as its current frame), which
 // keeps all of a warp's ~11 KB of loads independent and in flight together.
-__global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
+__global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (gw >= p.n_windows * p.T) return;
@@ -93,38 +93,38 @@ __global__ void __launch_bounds__(kThreads) k_feature_fuse(const FuseParams p) {
     const bool has_diff = p.diff_dim[m] > 0;
 
     if (kind == TAG_KIND_COSINE) {
-      // dim <= 1024 and even (checked on the host): 16 float2 per lane, coalesced 256 B per warp load
-      float2 a[16], b[16];
+      // dim even (checked on the host). Two passes over the row pair instead of holding it in registers: the second
+      // pass re-reads through L1/L2, and the kernel keeps 4+ CTAs per SM (it is latency-, not bandwidth-bound).
       float sa = 0.f, sb = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = 2 * lane + 64 * j;
-        a[j] = (i < dim) ? __ldg(reinterpret_cast<const float2*>(xc + i)) : make_float2(0.f, 0.f);
-        b[j] = (i < dim && has_diff) ? __ldg(reinterpret_cast<const float2*>(xp + i)) : make_float2(0.f, 0.f);
-        sa = fmaf(a[j].x, a[j].x, sa); sa = fmaf(a[j].y, a[j].y, sa);
-        sb = fmaf(b[j].x, b[j].x, sb); sb = fmaf(b[j].y, b[j].y, sb);
+#pragma unroll 4
+      for (int i = 2 * lane; i < dim; i += 64) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(xc + i));
+        sa = fmaf(a.x, a.x, sa); sa = fmaf(a.y, a.y, sa);
+        if (has_diff) {
+          const float2 b = __ldg(reinterpret_cast<const float2*>(xp + i));
+          sb = fmaf(b.x, b.x, sb); sb = fmaf(b.y, b.y, sb);
+        }
       }
       const float inv = 1.0f / fmaxf(sqrtf(warp_sum(sa)), 1e-12f);          // F.normalize eps
       const float invp = 1.0f / fmaxf(sqrtf(warp_sum(sb)), 1e-12f);
       const bool vec32 = out != nullptr && ((p.D | ro | dofs) & 1) == 0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = 2 * lane + 64 * j;
-        if (i < dim) {
-          const float r0 = nz(a[j].x, ro + i), r1 = nz(a[j].y, ro + i + 1);
+#pragma unroll 2
+      for (int i = 2 * lane; i < dim; i += 64) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(xc + i));
+        const float r0 = nz(a.x, ro + i), r1 = nz(a.y, ro + i + 1);
+        if (out) {
+          if (vec32) *reinterpret_cast<float2*>(out + ro + i) = make_float2(r0, r1);
+          else { out[ro + i] = r0; out[ro + i + 1] = r1; }
+        }
+        if (out16) *reinterpret_cast<__half2*>(out16 + ro16 + i) = __floats2half2_rn(r0, r1);
+        if (has_diff) {
+          const float2 b = __ldg(reinterpret_cast<const float2*>(xp + i));
+          const float d0 = nz(a.x * inv - b.x * invp, dofs + i), d1 = nz(a.y * inv - b.y * invp, dofs + i + 1);
           if (out) {
-            if (vec32) *reinterpret_cast<float2*>(out + ro + i) = make_float2(r0, r1);
-            else { out[ro + i] = r0; out[ro + i + 1] = r1; }
+            if (vec32) *reinterpret_cast<float2*>(out + dofs + i) = make_float2(d0, d1);
+            else { out[dofs + i] = d0; out[dofs + i + 1] = d1; }
           }
-          if (out16) *reinterpret_cast<__half2*>(out16 + ro16 + i) = __floats2half2_rn(r0, r1);
-          if (has_diff) {
-            const float d0 = nz(a[j].x * inv - b[j].x * invp, dofs + i), d1 = nz(a[j].y * inv - b[j].y * invp, dofs + i + 1);
-            if (out) {
-              if (vec32) *reinterpret_cast<float2*>(out + dofs + i) = make_float2(d0, d1);
-              else { out[dofs + i] = d0; out[dofs + i + 1] = d1; }
-            }
-            if (out16) *reinterpret_cast<__half2*>(out16 + do16 + i) = __floats2half2_rn(d0, d1);
-          }
+          if (out16) *reinterpret_cast<__half2*>(out16 + do16 + i) = __floats2half2_rn(d0, d1);
         }
       }
     } else if (kind == TAG_KIND_ROTMAT) {

@@ -105,6 +105,8 @@ struct GemmTC {
   int act;
   const float* gn_gamma;          // non-null: fuse GroupNorm(1,256) over each (T x 256) window after the activation
   const float* gn_beta;
+  const float* ln_gamma;          // non-null: fuse LayerNorm over the 256 output columns after bias + fp32 residual;
+  const float* ln_beta;           //   needs N == 256, res32, C32 (may alias res32) and C16
 };
 struct TcContext;   // opaque: driver entry points + cached tensor maps
 TcContext* tc_context_create(int device, char* err, int errlen);

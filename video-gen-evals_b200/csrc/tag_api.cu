@@ -369,18 +369,17 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
     { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_attention<__half>(QKV, ATT, W, T + 1, h->cfg.n_heads, s)); }
     GemmTC o{};
     o.A = ATT; o.M = R2; o.lda = kD; o.W = L.out_w16; o.N = kD; o.K = kD; o.taps = 1; o.dil = 1; o.T = 1; o.bias = L.out_b;
-    o.res32 = h->X; o.C32 = h->TMP;
+    // out-proj + bias + residual + LayerNorm(norm1) in one kernel, in place over the fp32 token stream
+    o.res32 = h->X; o.C32 = h->X; o.C16 = X16; o.ldc = kD; o.ln_gamma = L.n1_g; o.ln_beta = L.n1_b;
     rc = gemm_tc_run(h, s, o, 2.0 * R2 * kD * kD); if (rc) return rc;
-    { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_layernorm<__half>(h->TMP, L.n1_g, L.n1_b, h->X, X16, R2, s)); }
     GemmTC f1{};
     f1.A = X16; f1.M = R2; f1.lda = kD; f1.W = L.l1_w16; f1.N = F; f1.K = kD; f1.taps = 1; f1.dil = 1; f1.T = 1; f1.bias = L.l1_b;
     f1.C16 = FF; f1.ldc = F; f1.act = 2;
     rc = gemm_tc_run(h, s, f1, 2.0 * R2 * F * kD); if (rc) return rc;
     GemmTC f2{};
     f2.A = FF; f2.M = R2; f2.lda = F; f2.W = L.l2_w16; f2.N = kD; f2.K = F; f2.taps = 1; f2.dil = 1; f2.T = 1; f2.bias = L.l2_b;
-    f2.res32 = h->X; f2.C32 = h->TMP;
+    f2.res32 = h->X; f2.C32 = h->X; f2.C16 = X16; f2.ldc = kD; f2.ln_gamma = L.n2_g; f2.ln_beta = L.n2_b;
     rc = gemm_tc_run(h, s, f2, 2.0 * R2 * F * kD); if (rc) return rc;
-    { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_layernorm<__half>(h->TMP, L.n2_g, L.n2_b, h->X, X16, R2, s)); }
   }
   { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_finalize(h->X, W, T + 1, seq, frame, tokens, tcw, s)); }
   return TAG_OK;
@@ -829,7 +828,8 @@ int tag_debug_gemm_f32(tag_handle* h, const float* A, int32_t lda, const float* 
 
 int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, int64_t M, int32_t N, int32_t K,
                       int32_t taps, int32_t dil, int32_t T, const float* bias, const void* res16, const float* res32,
-                      void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta, void* stream) {
+                      void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta,
+                      const float* ln_gamma, const float* ln_beta, void* stream) {
   if (!h) return TAG_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if (!h->tc) {
@@ -839,7 +839,7 @@ int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, 
   GemmTC g{};
   g.A = (const __half*)A; g.M = M; g.lda = lda; g.W = (const __half*)W; g.N = N; g.K = K; g.taps = taps; g.dil = dil; g.T = T;
   g.bias = bias; g.res16 = (const __half*)res16; g.ldr = N; g.res32 = res32; g.C16 = (__half*)C16; g.ldc = N; g.C32 = C32; g.act = act;
-  g.gn_gamma = gn_gamma; g.gn_beta = gn_beta;
+  g.gn_gamma = gn_gamma; g.gn_beta = gn_beta; g.ln_gamma = ln_gamma; g.ln_beta = ln_beta;
   h->err[0] = 0;
   return gemm_tc_run(h, (cudaStream_t)stream, g, 2.0 * (double)M * N * K * taps);
 }
