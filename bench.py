@@ -250,7 +250,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     l1 = launches()
-    prof = (__import__("ctypes").c_double * 9)()
+    prof = (__import__("ctypes").c_double * 12)()
     pkg._lib.check(h, lib.tag_get_profile(h, prof), "tag_get_profile")
     pkg._lib.check(h, lib.tag_set_profiling(h, 0), "tag_set_profiling")
     clocks = sampler.stop() if rank == 0 else None
@@ -279,7 +279,7 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        other_ms, _, other_n, conv_ms, conv_flops, conv_n, og_ms, og_flops, og_n = [float(x) for x in prof]
+        other_ms, _, other_n, conv_ms, conv_flops, conv_n, og_ms, og_flops, og_n, k1_ms, k1_bytes, k1_n = [float(x) for x in prof]
         achieved = (conv_flops / conv_n) / (conv_ms / conv_n * 1e-3) / 1e12 if conv_n > 0 and conv_ms > 0 else None
         tc_mode = args.precision == "fp16_tc"
         roof_peak = pk["tflops"] if tc_mode else 75.0
@@ -303,7 +303,11 @@ def main():
                          "frac": (achieved / roof_peak) if achieved else None, "traffic": traffic,
                          "peak_source": pk["source"] if tc_mode else "nominal fp32 CUDA-core peak (~75 TFLOP/s), fp32 mode only",
                          "launches_sampled": int(conv_n), "mean_launch_ms": conv_ms / conv_n if conv_n else None,
-                         "share_of_step": {"conv_gemm_ms": conv_ms, "other_gemm_ms": og_ms, "non_gemm_ms": other_ms},
+                         "share_of_step": {"conv_gemm_ms": conv_ms, "other_gemm_ms": og_ms, "feature_fuse_ms": k1_ms,
+                                           "other_kernels_ms": other_ms},
+                         "feature_fuse_hbm": {"bound": "hbm", "achieved": (k1_bytes / (k1_ms * 1e-3) / 1e9) if k1_ms > 0 else None,
+                                              "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                              "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if k1_ms > 0 else None},
                          "whole_encoder_tflops": value / world * (n_windows / args.videos) * GFLOP_PER_WINDOW / 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(2 * args.videos * 4),
                     "steps": e2e_steps},

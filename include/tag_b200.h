@@ -148,11 +148,11 @@ int tag_tcl_forward(tag_handle* h, const float* z, const int32_t* targets, int64
 
 /* --- introspection used by bench.py: kernels launched through this handle since creation; with
  *     profiling on, every encoder kernel is bracketed by CUDA events on the caller's stream and
- *     out9 = {other: ms, flops, launches | conv GEMM: ms, flops, launches | other GEMM: ms, flops,
- *     launches}, accumulated since tag_set_profiling(h, 1). */
+ *     out12 = {other: ms, -, launches | conv GEMM: ms, flops, launches | other GEMM: ms, flops, launches |
+ *     feature fuse: ms, algorithmic bytes, launches}, accumulated since tag_set_profiling(h, 1). */
 int64_t tag_launch_count(const tag_handle* h);
 int tag_set_profiling(tag_handle* h, int32_t on);
-int tag_get_profile(tag_handle* h, double* out9);
+int tag_get_profile(tag_handle* h, double* out12);
 
 /* --- test hooks: the two GEMM kernels in isolation (tests/test_gemm_gpu.py).
  *     C = act(sum_taps A[row+shift] W^T + bias + res); fp32: W [N, ldw]; tensor-core: A/W/res16/C16

@@ -34,7 +34,7 @@ struct LayerWeights {               // nn.TransformerEncoderLayer (model.py:145)
   __half *in_w16, *out_w16, *l1_w16, *l2_w16;
 };
 
-struct ProfEvent { cudaEvent_t a, b; double flops; int kind; };   // kind: 0 other, 1 conv GEMM, 2 other GEMM
+struct ProfEvent { cudaEvent_t a, b; double flops; int kind; };   // kind: 0 other, 1 conv GEMM, 2 other GEMM, 3 feature fuse (K1)
 
 }  // namespace
 
@@ -71,7 +71,7 @@ struct tag_handle {
   bool profiling = false;
   std::vector<ProfEvent> prof;
   size_t prof_used = 0;
-  double prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // per kind: ms, flops, launches
+  double prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per kind: ms, flops (K1: bytes), launches
   int* col_tab = nullptr;           // device [M][6] column map fp32 feats -> fp16 operand layout
   float* zs_scale = nullptr;        // [D] z-score tables, rebuilt from (mean, std) at every feature-fuse call
   float* zs_shift = nullptr;
@@ -742,7 +742,7 @@ int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean,
     p.feats = tc ? nullptr : h->feats;
     p.feats16 = tc ? h->feats16 : nullptr;
     p.flags = flags_out;
-    { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_feature_fuse(p, s)); }
+    { ProfScope ps(h, s, 3, (double)W * T * ((double)h->raw_total * 4 + (tc ? (double)h->D16 * 2 : (double)h->D * 4))); LAUNCH_TRY(h, launch_feature_fuse(p, s)); }
     float* seq = seq_embed + w0 * kD;
     float* fr = frame_embeds ? frame_embeds + w0 * S * kD : nullptr;
     float* tk = tokens ? tokens + w0 * S * kD : nullptr;
@@ -859,12 +859,13 @@ int tag_set_profiling(tag_handle* h, int32_t on) {
   return TAG_OK;
 }
 
-int tag_get_profile(tag_handle* h, double* out9) {
+int tag_get_profile(tag_handle* h, double* out12) {
+  double* out9 = out12;
   if (!h || !out9) return TAG_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = prof_collect(h);
   if (rc) return rc;
-  for (int i = 0; i < 9; ++i) out9[i] = h->prof_acc[i];
+  for (int i = 0; i < 12; ++i) out9[i] = h->prof_acc[i];
   return TAG_OK;
 }
 
