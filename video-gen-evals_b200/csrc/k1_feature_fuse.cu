@@ -12,8 +12,8 @@
 //   utils.py:472-514  z-score (x-mean)/(std+1e-6) and concat
 //
 // HBM-bound: per (window, frame) reads sum(raw_dims)*4 B and writes D*4 B (fp32 feats) and/or D16*2 B
-// (padded fp16 operand for the tensor-core encoder). One warp per (window, frame), 8 consecutive frames per
-// CTA; the previous frame is re-read through L1/L2, so DRAM sees each source frame about once per window.
+// (padded fp16 operand for the tensor-core encoder). One warp per (window, 8 consecutive frames); overlapping
+// windows re-read source frames through L2, so DRAM sees each source frame about once or twice per batch.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -51,177 +51,197 @@ __global__ void k_zscore_table(const float* __restrict__ mean, const float* __re
   }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// One warp per (window, frame): every reduction (cosine norms, keypoint centre / scale / 2x2 correlation) is a
-// warp shuffle, so there is no block barrier and no shared memory; the previous frame's quantities are recomputed
-// from its row (an L1/L2 hit: the neighbouring warp of the same CTA streams that row as its current frame), which
-// keeps all of a warp's ~11 KB of loads independent and in flight together.
+
+// One warp per (window, block of kF = 8 consecutive frames). Every reduction (cosine norms, keypoint centre / scale /
+// 2x2 correlation) is a warp shuffle: no block barrier, no shared memory. For the wide cosine modalities (vit / clip /
+// dino: 70 % of the bytes) the warp first computes the kF+1 row norms, then walks the columns in chunks of 64: the four
+// z-score table entries of a column pair are loaded ONCE per chunk and the previous frame's values are carried in
+// registers from one frame to the next, so per output element the kernel issues one 8-byte load, ~5 FMAs and two
+// 4-byte stores. The small modalities (rotations, betas, keypoints: 346 of 1370 input floats) are handled per frame.
+constexpr int kF = 8;
+
+template <bool O32, bool O16>
+__device__ __forceinline__ void put1(float* out, __half* out16, int c32, int c16, float v) {
+  if (O32) out[c32] = v;
+  if (O16) out16[c16] = __float2half_rn(v);
+}
+
+template <bool O32, bool O16>
 __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p) {
   const int lane = threadIdx.x & 31;
+  const int blocks_per_win = (p.T + kF - 1) / kF;
   const int64_t gw = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (gw >= p.n_windows * p.T) return;
-  const int64_t w = gw / p.T;
-  const int t = (int)(gw - w * p.T);
+  if (gw >= p.n_windows * blocks_per_win) return;
+  const int64_t w = gw / blocks_per_win;
+  const int t0 = (int)(gw - w * blocks_per_win) * kF;
+  const int nf = min(kF, p.T - t0);                    // frames of this block
   const int vid = p.win_video[w];
   const int start = p.win_start[w];
   const int64_t f0 = p.frame_offset[vid];
   const int L = (int)(p.frame_offset[vid + 1] - f0);
   const Norm nz{p.mean, p.stdv};          // (scale, shift) tables when stats are given
-  const int64_t cur = f0 + src_frame(start, t, L);
-  const int64_t prv = (t == 0) ? cur : f0 + src_frame(start, t - 1, L);
-  // pull every modality's current and previous rows towards L2 now: the per-modality phases below are dependent
-  // (reduce, then write), so without this each phase pays its own DRAM round trip
-#pragma unroll 1
-  for (int m = 0; m < p.M; ++m) {
-    const int bytes = p.raw_dim[m] * 4;
-    const char* c0 = reinterpret_cast<const char*>(p.src[m] + cur * p.raw_dim[m]);
-    const char* p0 = reinterpret_cast<const char*>(p.src[m] + prv * p.raw_dim[m]);
-    for (int o = lane * 128; o < bytes; o += 32 * 128) { prefetch_l2(c0 + o); prefetch_l2(p0 + o); }
-  }
-  float* out = p.feats ? p.feats + gw * p.D : nullptr;
-  __half* out16 = p.feats16 ? p.feats16 + gw * p.D16 : nullptr;
+  // source row of window frame t (t = t0-1 .. t0+nf-1); frame -1 of the window pairs with itself (zero delta)
+  auto row_of = [&](int t) -> int64_t { return f0 + src_frame(start, t < 0 ? 0 : t, L); };
+  float* outw = O32 ? p.feats + ((int64_t)w * p.T + t0) * p.D : nullptr;
+  __half* outw16 = O16 ? p.feats16 + ((int64_t)w * p.T + t0) * p.D16 : nullptr;
 
 #pragma unroll 1
   for (int m = 0; m < p.M; ++m) {
     const int dim = p.raw_dim[m];
-    const float* xc = p.src[m] + cur * dim;
-    const float* xp = p.src[m] + prv * dim;
+    const float* src = p.src[m];
     const int ro = p.raw_off[m], dofs = p.diff_off[m];
     const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
     const int kind = p.kind[m];
     const bool has_diff = p.diff_dim[m] > 0;
 
     if (kind == TAG_KIND_COSINE) {
-      // dim even (checked on the host). Two passes over the row pair instead of holding it in registers: the second
-      // pass re-reads through L1/L2, and the kernel keeps 4+ CTAs per SM (it is latency-, not bandwidth-bound).
-      float sa = 0.f, sb = 0.f;
+      // ---- pass 1: 1 / max(||row||, 1e-12) of rows t0-1 .. t0+nf-1  (F.normalize eps)
+      float inv[kF + 1];
+#pragma unroll
+      for (int f = 0; f <= kF; ++f) {
+        inv[f] = 0.f;
+        if (f <= nf && (f > 0 || has_diff)) {
+          const float* x = src + row_of(t0 + f - 1) * dim;
+          float ss = 0.f;
 #pragma unroll 4
-      for (int i = 2 * lane; i < dim; i += 64) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(xc + i));
-        sa = fmaf(a.x, a.x, sa); sa = fmaf(a.y, a.y, sa);
-        if (has_diff) {
-          const float2 b = __ldg(reinterpret_cast<const float2*>(xp + i));
-          sb = fmaf(b.x, b.x, sb); sb = fmaf(b.y, b.y, sb);
-        }
-      }
-      const float inv = 1.0f / fmaxf(sqrtf(warp_sum(sa)), 1e-12f);          // F.normalize eps
-      const float invp = 1.0f / fmaxf(sqrtf(warp_sum(sb)), 1e-12f);
-      const bool vec32 = out != nullptr && ((p.D | ro | dofs) & 1) == 0;
-#pragma unroll 2
-      for (int i = 2 * lane; i < dim; i += 64) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(xc + i));
-        const float r0 = nz(a.x, ro + i), r1 = nz(a.y, ro + i + 1);
-        if (out) {
-          if (vec32) *reinterpret_cast<float2*>(out + ro + i) = make_float2(r0, r1);
-          else { out[ro + i] = r0; out[ro + i + 1] = r1; }
-        }
-        if (out16) *reinterpret_cast<__half2*>(out16 + ro16 + i) = __floats2half2_rn(r0, r1);
-        if (has_diff) {
-          const float2 b = __ldg(reinterpret_cast<const float2*>(xp + i));
-          const float d0 = nz(a.x * inv - b.x * invp, dofs + i), d1 = nz(a.y * inv - b.y * invp, dofs + i + 1);
-          if (out) {
-            if (vec32) *reinterpret_cast<float2*>(out + dofs + i) = make_float2(d0, d1);
-            else { out[dofs + i] = d0; out[dofs + i + 1] = d1; }
+          for (int i = 2 * lane; i < dim; i += 64) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(x + i));
+            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
           }
-          if (out16) *reinterpret_cast<__half2*>(out16 + do16 + i) = __floats2half2_rn(d0, d1);
+          inv[f] = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
         }
       }
-    } else if (kind == TAG_KIND_ROTMAT) {
-      for (int i = lane; i < dim; i += 32) {
-        const float r = nz(__ldg(xc + i), ro + i);
-        if (out) out[ro + i] = r;
-        if (out16) out16[ro16 + i] = __float2half_rn(r);
-      }
-      const int J = dim / 9;
-      if (has_diff) {
-        for (int jn = lane; jn < J; jn += 32) {
-          float R[9], Q[9];
+      // ---- pass 2: column chunks; tables once per chunk, previous frame carried in registers
+      const bool vec32 = O32 && ((p.D | ro | dofs) & 1) == 0;
+#pragma unroll 1
+      for (int i = 2 * lane; i < dim; i += 64) {
+        float2 sr = make_float2(1.f, 1.f), hr = make_float2(0.f, 0.f), sd = sr, hd = hr;
+        if (nz.scale != nullptr) {
+          sr = make_float2(__ldg(nz.scale + ro + i), __ldg(nz.scale + ro + i + 1));
+          hr = make_float2(__ldg(nz.shift + ro + i), __ldg(nz.shift + ro + i + 1));
+          if (has_diff) {
+            sd = make_float2(__ldg(nz.scale + dofs + i), __ldg(nz.scale + dofs + i + 1));
+            hd = make_float2(__ldg(nz.shift + dofs + i), __ldg(nz.shift + dofs + i + 1));
+          }
+        }
+        float2 prev = make_float2(0.f, 0.f);
+        if (has_diff) {
+          prev = __ldg(reinterpret_cast<const float2*>(src + row_of(t0 - 1) * dim + i));
+          prev.x *= inv[0]; prev.y *= inv[0];
+        }
 #pragma unroll
-          for (int k = 0; k < 9; ++k) { R[k] = __ldg(xc + jn * 9 + k); Q[k] = __ldg(xp + jn * 9 + k); }
-          // Rrel = Q^T R  (utils.py:172), entries [i][j] = sum_k Q[k][i] R[k][j]
-          float E[9];
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
-          float tr = E[0] + E[4] + E[8];
-          tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
-          const float c = (tr - 1.f) / 2.f;
-          const float theta = acosf(c);
-          // 2 sin(theta) with theta in [0, pi]: sin = sqrt((1-c)(1+c)); 1-c is exact in fp32 near c = 1, so this is
-          // at least as accurate as sinf(acosf(c)) and costs one sqrt instead of a libm sine
-          const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
-          const float k = theta / den;
-          const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float d = nz(wv[k], dofs + jn * 3 + k);
-            if (out) out[dofs + jn * 3 + k] = d;
-            if (out16) out16[do16 + jn * 3 + k] = __float2half_rn(d);
+        for (int f = 0; f < kF; ++f) {
+          if (f < nf) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(src + row_of(t0 + f) * dim + i));
+            const float r0 = fmaf(a.x, sr.x, hr.x), r1 = fmaf(a.y, sr.y, hr.y);
+            float* o = outw + (int64_t)f * p.D;
+            __half* o16 = outw16 + (int64_t)f * p.D16;
+            if (O32) {
+              if (vec32) *reinterpret_cast<float2*>(o + ro + i) = make_float2(r0, r1);
+              else { o[ro + i] = r0; o[ro + i + 1] = r1; }
+            }
+            if (O16) *reinterpret_cast<__half2*>(o16 + ro16 + i) = __floats2half2_rn(r0, r1);
+            if (has_diff) {
+              const float2 cur = make_float2(a.x * inv[f + 1], a.y * inv[f + 1]);
+              const float d0 = fmaf(cur.x - prev.x, sd.x, hd.x), d1 = fmaf(cur.y - prev.y, sd.y, hd.y);
+              if (O32) {
+                if (vec32) *reinterpret_cast<float2*>(o + dofs + i) = make_float2(d0, d1);
+                else { o[dofs + i] = d0; o[dofs + i + 1] = d1; }
+              }
+              if (O16) *reinterpret_cast<__half2*>(o16 + do16 + i) = __floats2half2_rn(d0, d1);
+              prev = cur;
+            }
           }
         }
       }
-    } else if (kind == TAG_KIND_PLAIN) {
-      for (int i = lane; i < dim; i += 32) {
-        const float x = __ldg(xc + i);
-        const float r = nz(x, ro + i);
-        if (out) out[ro + i] = r;
-        if (out16) out16[ro16 + i] = __float2half_rn(r);
+      continue;
+    }
+
+    // ---- small modalities: per frame
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) {
+      const int t = t0 + f;
+      const float* xc = src + row_of(t) * dim;
+      const float* xp = src + row_of(t - 1) * dim;
+      float* out = O32 ? outw + (int64_t)f * p.D : nullptr;
+      __half* out16 = O16 ? outw16 + (int64_t)f * p.D16 : nullptr;
+      if (kind == TAG_KIND_ROTMAT) {
+        for (int i = lane; i < dim; i += 32) put1<O32, O16>(out, out16, ro + i, ro16 + i, nz(__ldg(xc + i), ro + i));
+        const int J = dim / 9;
         if (has_diff) {
-          const float d = nz(x - __ldg(xp + i), dofs + i);
-          if (out) out[dofs + i] = d;
-          if (out16) out16[do16 + i] = __float2half_rn(d);
+          for (int jn = lane; jn < J; jn += 32) {
+            float R[9], Q[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { R[k] = __ldg(xc + jn * 9 + k); Q[k] = __ldg(xp + jn * 9 + k); }
+            // Rrel = Q^T R  (utils.py:172), entries [i][j] = sum_k Q[k][i] R[k][j]
+            float E[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
+            float tr = E[0] + E[4] + E[8];
+            tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
+            const float c = (tr - 1.f) / 2.f;
+            const float theta = acosf(c);
+            // 2 sin(theta) with theta in [0, pi]: sin = sqrt((1-c)(1+c)); 1-c is exact in fp32 near c = 1, so this is
+            // at least as accurate as sinf(acosf(c)) and costs one sqrt instead of a libm sine
+            const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
+            const float k = theta / den;
+            const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) put1<O32, O16>(out, out16, dofs + jn * 3 + q, do16 + jn * 3 + q, nz(wv[q], dofs + jn * 3 + q));
+          }
         }
-      }
-    } else {  // TAG_KIND_PROCRUSTES: K = dim/2 <= 64 points, two per lane
-      for (int i = lane; i < dim; i += 32) {
-        const float r = nz(__ldg(xc + i), ro + i);
-        if (out) out[ro + i] = r;
-        if (out16) out16[ro16 + i] = __float2half_rn(r);
-      }
-      if (has_diff) {
-        const int K = dim / 2;
-        const int k0 = lane, k1 = lane + 32;
-        const bool a0 = k0 < K, a1 = k1 < K;
-        // centre + Frobenius-normalise one frame's points (utils.py:192-196)
-        auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
-          x0 = a0 ? __ldg(x + 2 * k0) : 0.f; y0 = a0 ? __ldg(x + 2 * k0 + 1) : 0.f;
-          x1 = a1 ? __ldg(x + 2 * k1) : 0.f; y1 = a1 ? __ldg(x + 2 * k1 + 1) : 0.f;
-          const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
-          x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
-          x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
-          const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
-          x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
-        };
-        float x0, y0, x1, y1, px0, py0, px1, py1;
-        load_norm(xc, x0, y0, x1, y1);
-        load_norm(xp, px0, py0, px1, py1);
-        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-        if (t > 0) {
-          // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
-          const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
-          const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
-          if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
-          // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
-          const float ry = h10 - h01, rx = h00 + h11;
-          const float rr = ry * ry + rx * rx;
-          const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
-          const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
-          // X @ R with R = [[c, s], [-s, c]]  (== Vh @ U.T for det(H) > 0)
-          d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
-          d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
+      } else if (kind == TAG_KIND_PLAIN) {
+        for (int i = lane; i < dim; i += 32) {
+          const float x = __ldg(xc + i);
+          put1<O32, O16>(out, out16, ro + i, ro16 + i, nz(x, ro + i));
+          if (has_diff) put1<O32, O16>(out, out16, dofs + i, do16 + i, nz(x - __ldg(xp + i), dofs + i));
         }
-        if (a0) {
-          const float e0 = nz(d00, dofs + 2 * k0), e1 = nz(d01, dofs + 2 * k0 + 1);
-          if (out) { out[dofs + 2 * k0] = e0; out[dofs + 2 * k0 + 1] = e1; }
-          if (out16) { out16[do16 + 2 * k0] = __float2half_rn(e0); out16[do16 + 2 * k0 + 1] = __float2half_rn(e1); }
-        }
-        if (a1) {
-          const float e0 = nz(d10, dofs + 2 * k1), e1 = nz(d11, dofs + 2 * k1 + 1);
-          if (out) { out[dofs + 2 * k1] = e0; out[dofs + 2 * k1 + 1] = e1; }
-          if (out16) { out16[do16 + 2 * k1] = __float2half_rn(e0); out16[do16 + 2 * k1 + 1] = __float2half_rn(e1); }
+      } else {  // TAG_KIND_PROCRUSTES: K = dim/2 <= 64 points, two per lane
+        for (int i = lane; i < dim; i += 32) put1<O32, O16>(out, out16, ro + i, ro16 + i, nz(__ldg(xc + i), ro + i));
+        if (has_diff) {
+          const int K = dim / 2;
+          const int k0 = lane, k1 = lane + 32;
+          const bool a0 = k0 < K, a1 = k1 < K;
+          // centre + Frobenius-normalise one frame's points (utils.py:192-196)
+          auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
+            x0 = a0 ? __ldg(x + 2 * k0) : 0.f; y0 = a0 ? __ldg(x + 2 * k0 + 1) : 0.f;
+            x1 = a1 ? __ldg(x + 2 * k1) : 0.f; y1 = a1 ? __ldg(x + 2 * k1 + 1) : 0.f;
+            const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
+            x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
+            x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
+            const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
+            x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
+          };
+          float x0, y0, x1, y1, px0, py0, px1, py1;
+          load_norm(xc, x0, y0, x1, y1);
+          load_norm(xp, px0, py0, px1, py1);
+          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+          if (t > 0) {
+            // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
+            const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
+            const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
+            if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+            // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
+            const float ry = h10 - h01, rx = h00 + h11;
+            const float rr = ry * ry + rx * rx;
+            const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
+            const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
+            // X @ R with R = [[c, s], [-s, c]]  (== Vh @ U.T for det(H) > 0)
+            d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
+            d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
+          }
+          if (a0) {
+            put1<O32, O16>(out, out16, dofs + 2 * k0, do16 + 2 * k0, nz(d00, dofs + 2 * k0));
+            put1<O32, O16>(out, out16, dofs + 2 * k0 + 1, do16 + 2 * k0 + 1, nz(d01, dofs + 2 * k0 + 1));
+          }
+          if (a1) {
+            put1<O32, O16>(out, out16, dofs + 2 * k1, do16 + 2 * k1, nz(d10, dofs + 2 * k1));
+            put1<O32, O16>(out, out16, dofs + 2 * k1 + 1, do16 + 2 * k1 + 1, nz(d11, dofs + 2 * k1 + 1));
+          }
         }
       }
     }
@@ -237,7 +257,11 @@ cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* sca
 
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
   if (p.n_windows <= 0) return cudaSuccess;
-  const int64_t warps = p.n_windows * p.T;
-  k_feature_fuse<<<(unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32)), kThreads, 0, s>>>(p);
+  const int64_t warps = p.n_windows * ((p.T + kF - 1) / kF);
+  const unsigned grid = (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
+  if (p.feats != nullptr && p.feats16 != nullptr) k_feature_fuse<true, true><<<grid, kThreads, 0, s>>>(p);
+  else if (p.feats != nullptr) k_feature_fuse<true, false><<<grid, kThreads, 0, s>>>(p);
+  else if (p.feats16 != nullptr) k_feature_fuse<false, true><<<grid, kThreads, 0, s>>>(p);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
