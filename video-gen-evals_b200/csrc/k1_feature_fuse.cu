@@ -68,7 +68,7 @@ __device__ __forceinline__ void put1(float* out, __half* out16, int c32, int c16
 }
 
 template <bool O32, bool O16>
-__global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p) {
+__global__ void __launch_bounds__(kThreads, 3) k_feature_fuse(const FuseParams p) {
   const int lane = threadIdx.x & 31;
   const int blocks_per_win = (p.T + kF - 1) / kF;
   const int64_t gw = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -85,6 +85,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
   auto row_of = [&](int t) -> int64_t { return f0 + src_frame(start, t < 0 ? 0 : t, L); };
   float* outw = O32 ? p.feats + ((int64_t)w * p.T + t0) * p.D : nullptr;
   __half* outw16 = O16 ? p.feats16 + ((int64_t)w * p.T + t0) * p.D16 : nullptr;
+  // the small modalities are walked frame by frame further down (dependent load -> math -> store phases): pull their
+  // rows of all kF+1 frames towards L2 now so those phases do not each pay a DRAM round trip
+#pragma unroll 1
+  for (int m = 0; m < p.M; ++m) {
+    if (p.kind[m] == TAG_KIND_COSINE) continue;
+    const int bytes = p.raw_dim[m] * 4;
+    const int lines = (bytes + 127) / 128 + 1;
+    for (int k = lane; k < lines * (nf + 1); k += 32) {
+      const int f = k / lines, ln = k - f * lines;
+      const char* a = reinterpret_cast<const char*>(p.src[m] + row_of(t0 + f - 1) * p.raw_dim[m]) + ln * 128;
+      if (ln * 128 < bytes + 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+  }
 
 #pragma unroll 1
   for (int m = 0; m < p.M; ++m) {
@@ -96,25 +109,27 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
     const bool has_diff = p.diff_dim[m] > 0;
 
     if (kind == TAG_KIND_COSINE) {
-      // ---- pass 1: 1 / max(||row||, 1e-12) of rows t0-1 .. t0+nf-1  (F.normalize eps)
+      // ---- pass 1: 1 / max(||row||, 1e-12) of rows t0-1 .. t0+nf-1  (F.normalize eps). All rows advance together
+      // through the columns, so each lane keeps kF+1 (x2 with the unroll) independent 8-byte loads in flight.
+      const float* rp[kF + 1];
       float inv[kF + 1];
 #pragma unroll
-      for (int f = 0; f <= kF; ++f) {
-        inv[f] = 0.f;
-        if (f <= nf && (f > 0 || has_diff)) {
-          const float* x = src + row_of(t0 + f - 1) * dim;
-          float ss = 0.f;
-#pragma unroll 4
-          for (int i = 2 * lane; i < dim; i += 64) {
-            const float2 a = __ldg(reinterpret_cast<const float2*>(x + i));
-            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
+      for (int f = 0; f <= kF; ++f) { rp[f] = src + row_of(f <= nf ? t0 + f - 1 : t0) * dim; inv[f] = 0.f; }
+#pragma unroll 2
+      for (int i = 2 * lane; i < dim; i += 64) {
+#pragma unroll
+        for (int f = 0; f <= kF; ++f) {
+          if (f <= nf && (f > 0 || has_diff)) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(rp[f] + i));
+            inv[f] = fmaf(a.x, a.x, inv[f]); inv[f] = fmaf(a.y, a.y, inv[f]);
           }
-          inv[f] = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
         }
       }
+#pragma unroll
+      for (int f = 0; f <= kF; ++f) inv[f] = 1.0f / fmaxf(sqrtf(warp_sum(inv[f])), 1e-12f);
       // ---- pass 2: column chunks; tables once per chunk, previous frame carried in registers
       const bool vec32 = O32 && ((p.D | ro | dofs) & 1) == 0;
-#pragma unroll 1
+#pragma unroll 2
       for (int i = 2 * lane; i < dim; i += 64) {
         float2 sr = make_float2(1.f, 1.f), hr = make_float2(0.f, 0.f), sd = sr, hd = hr;
         if (nz.scale != nullptr) {
@@ -127,13 +142,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
         }
         float2 prev = make_float2(0.f, 0.f);
         if (has_diff) {
-          prev = __ldg(reinterpret_cast<const float2*>(src + row_of(t0 - 1) * dim + i));
+          prev = __ldg(reinterpret_cast<const float2*>(rp[0] + i));
           prev.x *= inv[0]; prev.y *= inv[0];
         }
 #pragma unroll
         for (int f = 0; f < kF; ++f) {
           if (f < nf) {
-            const float2 a = __ldg(reinterpret_cast<const float2*>(src + row_of(t0 + f) * dim + i));
+            const float2 a = __ldg(reinterpret_cast<const float2*>(rp[f + 1] + i));
             const float r0 = fmaf(a.x, sr.x, hr.x), r1 = fmaf(a.y, sr.y, hr.y);
             float* o = outw + (int64_t)f * p.D;
             __half* o16 = outw16 + (int64_t)f * p.D16;
