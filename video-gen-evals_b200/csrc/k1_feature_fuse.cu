@@ -59,7 +59,9 @@ __global__ void k_zscore_table(const float* __restrict__ mean, const float* __re
 // z-score table entries of a column pair are loaded ONCE per chunk and the previous frame's values are carried in
 // registers from one frame to the next, so per output element the kernel issues one 8-byte load, ~5 FMAs and two
 // 4-byte stores. The small modalities (rotations, betas, keypoints: 346 of 1370 input floats) are handled per frame.
-constexpr int kF = 8;
+// Two launches per call: the cosine modalities with KF = 8 frames per warp, everything else with KF = 2 (measured:
+// run together in one warp the two halves take 3.1 ms per 12.5k windows, separately 1.3 + 0.9 ms — the small
+// modalities are a chain of dependent load -> shuffle -> store phases that wants many short warps).
 
 template <bool O32, bool O16>
 __device__ __forceinline__ void put1(float* out, __half* out16, int c32, int c16, float v) {
@@ -67,8 +69,8 @@ __device__ __forceinline__ void put1(float* out, __half* out16, int c32, int c16
   if (O16) out16[c16] = __float2half_rn(v);
 }
 
-template <bool O32, bool O16>
-__global__ void __launch_bounds__(kThreads, 3) k_feature_fuse(const FuseParams p) {
+template <bool O32, bool O16, bool COSINE_PART, int kF>
+__global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p) {
   const int lane = threadIdx.x & 31;
   const int blocks_per_win = (p.T + kF - 1) / kF;
   const int64_t gw = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -85,19 +87,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_feature_fuse(const FuseParams p
   auto row_of = [&](int t) -> int64_t { return f0 + src_frame(start, t < 0 ? 0 : t, L); };
   float* outw = O32 ? p.feats + ((int64_t)w * p.T + t0) * p.D : nullptr;
   __half* outw16 = O16 ? p.feats16 + ((int64_t)w * p.T + t0) * p.D16 : nullptr;
-  // the small modalities are walked frame by frame further down (dependent load -> math -> store phases): pull their
-  // rows of all kF+1 frames towards L2 now so those phases do not each pay a DRAM round trip
-#pragma unroll 1
-  for (int m = 0; m < p.M; ++m) {
-    if (p.kind[m] == TAG_KIND_COSINE) continue;
-    const int bytes = p.raw_dim[m] * 4;
-    const int lines = (bytes + 127) / 128 + 1;
-    for (int k = lane; k < lines * (nf + 1); k += 32) {
-      const int f = k / lines, ln = k - f * lines;
-      const char* a = reinterpret_cast<const char*>(p.src[m] + row_of(t0 + f - 1) * p.raw_dim[m]) + ln * 128;
-      if (ln * 128 < bytes + 127) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-    }
-  }
 
 #pragma unroll 1
   for (int m = 0; m < p.M; ++m) {
@@ -107,29 +96,28 @@ __global__ void __launch_bounds__(kThreads, 3) k_feature_fuse(const FuseParams p
     const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
     const int kind = p.kind[m];
     const bool has_diff = p.diff_dim[m] > 0;
+    if ((kind == TAG_KIND_COSINE) != COSINE_PART) continue;
 
     if (kind == TAG_KIND_COSINE) {
-      // ---- pass 1: 1 / max(||row||, 1e-12) of rows t0-1 .. t0+nf-1  (F.normalize eps). All rows advance together
-      // through the columns, so each lane keeps kF+1 (x2 with the unroll) independent 8-byte loads in flight.
-      const float* rp[kF + 1];
+      // ---- pass 1: 1 / max(||row||, 1e-12) of rows t0-1 .. t0+nf-1  (F.normalize eps)
       float inv[kF + 1];
 #pragma unroll
-      for (int f = 0; f <= kF; ++f) { rp[f] = src + row_of(f <= nf ? t0 + f - 1 : t0) * dim; inv[f] = 0.f; }
-#pragma unroll 2
-      for (int i = 2 * lane; i < dim; i += 64) {
-#pragma unroll
-        for (int f = 0; f <= kF; ++f) {
-          if (f <= nf && (f > 0 || has_diff)) {
-            const float2 a = __ldg(reinterpret_cast<const float2*>(rp[f] + i));
-            inv[f] = fmaf(a.x, a.x, inv[f]); inv[f] = fmaf(a.y, a.y, inv[f]);
+      for (int f = 0; f <= kF; ++f) {
+        inv[f] = 0.f;
+        if (f <= nf && (f > 0 || has_diff)) {
+          const float* x = src + row_of(t0 + f - 1) * dim;
+          float ss = 0.f;
+#pragma unroll 4
+          for (int i = 2 * lane; i < dim; i += 64) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(x + i));
+            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
           }
+          inv[f] = 1.0f / fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
         }
       }
-#pragma unroll
-      for (int f = 0; f <= kF; ++f) inv[f] = 1.0f / fmaxf(sqrtf(warp_sum(inv[f])), 1e-12f);
       // ---- pass 2: column chunks; tables once per chunk, previous frame carried in registers
       const bool vec32 = O32 && ((p.D | ro | dofs) & 1) == 0;
-#pragma unroll 2
+#pragma unroll 1
       for (int i = 2 * lane; i < dim; i += 64) {
         float2 sr = make_float2(1.f, 1.f), hr = make_float2(0.f, 0.f), sd = sr, hd = hr;
         if (nz.scale != nullptr) {
@@ -142,13 +130,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_feature_fuse(const FuseParams p
         }
         float2 prev = make_float2(0.f, 0.f);
         if (has_diff) {
-          prev = __ldg(reinterpret_cast<const float2*>(rp[0] + i));
+          prev = __ldg(reinterpret_cast<const float2*>(src + row_of(t0 - 1) * dim + i));
           prev.x *= inv[0]; prev.y *= inv[0];
         }
 #pragma unroll
         for (int f = 0; f < kF; ++f) {
           if (f < nf) {
-            const float2 a = __ldg(reinterpret_cast<const float2*>(rp[f + 1] + i));
+            const float2 a = __ldg(reinterpret_cast<const float2*>(src + row_of(t0 + f) * dim + i));
             const float r0 = fmaf(a.x, sr.x, hr.x), r1 = fmaf(a.y, sr.y, hr.y);
             float* o = outw + (int64_t)f * p.D;
             __half* o16 = outw16 + (int64_t)f * p.D16;
@@ -272,11 +260,23 @@ cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* sca
 
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
   if (p.n_windows <= 0) return cudaSuccess;
-  const int64_t warps = p.n_windows * ((p.T + kF - 1) / kF);
-  const unsigned grid = (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
-  if (p.feats != nullptr && p.feats16 != nullptr) k_feature_fuse<true, true><<<grid, kThreads, 0, s>>>(p);
-  else if (p.feats != nullptr) k_feature_fuse<true, false><<<grid, kThreads, 0, s>>>(p);
-  else if (p.feats16 != nullptr) k_feature_fuse<false, true><<<grid, kThreads, 0, s>>>(p);
-  else return cudaErrorInvalidValue;
+  bool any_cos = false, any_small = false;
+  for (int m = 0; m < p.M; ++m) { if (p.kind[m] == TAG_KIND_COSINE) any_cos = true; else any_small = true; }
+  auto grid_for = [&](int kf) {
+    const int64_t warps = p.n_windows * ((p.T + kf - 1) / kf);
+    return (unsigned)((warps + kThreads / 32 - 1) / (kThreads / 32));
+  };
+  constexpr int KC = 8, KS = 2;
+  if (p.feats == nullptr && p.feats16 == nullptr) return cudaErrorInvalidValue;
+  if (any_cos) {
+    if (p.feats != nullptr && p.feats16 != nullptr) k_feature_fuse<true, true, true, KC><<<grid_for(KC), kThreads, 0, s>>>(p);
+    else if (p.feats != nullptr) k_feature_fuse<true, false, true, KC><<<grid_for(KC), kThreads, 0, s>>>(p);
+    else k_feature_fuse<false, true, true, KC><<<grid_for(KC), kThreads, 0, s>>>(p);
+  }
+  if (any_small) {
+    if (p.feats != nullptr && p.feats16 != nullptr) k_feature_fuse<true, true, false, KS><<<grid_for(KS), kThreads, 0, s>>>(p);
+    else if (p.feats != nullptr) k_feature_fuse<true, false, false, KS><<<grid_for(KS), kThreads, 0, s>>>(p);
+    else k_feature_fuse<false, true, false, KS><<<grid_for(KS), kThreads, 0, s>>>(p);
+  }
   return cudaGetLastError();
 }

@@ -26,6 +26,12 @@ struct FuseParams {
 };
 cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* scale, float* shift, int D, cudaStream_t s);
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s);
+// kernels launched by launch_feature_fuse (one for the cosine modalities, one for the rest)
+inline int feature_fuse_launches(const FuseParams& p) {
+  bool c = false, o = false;
+  for (int m = 0; m < p.M; ++m) { if (p.kind[m] == TAG_KIND_COSINE) c = true; else o = true; }
+  return (c ? 1 : 0) + (o ? 1 : 0);
+}
 
 // ------------------------------------------------------------------ K3 / K4 / N1 / N2
 cudaError_t launch_centroid_accumulate(const float* z, const int32_t* labels, int64_t n, int C,

@@ -684,6 +684,7 @@ int tag_feature_fuse(tag_handle* h, const tag_videos* vids, const float* mean, c
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   if (mean) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
   LAUNCH_TRY(h, launch_feature_fuse(p, (cudaStream_t)stream));
+  h->launches += feature_fuse_launches(p) - 1;
   return TAG_OK;
 }
 
@@ -742,7 +743,7 @@ int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean,
     p.feats = tc ? nullptr : h->feats;
     p.feats16 = tc ? h->feats16 : nullptr;
     p.flags = flags_out;
-    { ProfScope ps(h, s, 3, (double)W * T * ((double)h->raw_total * 4 + (tc ? (double)h->D16 * 2 : (double)h->D * 4))); LAUNCH_TRY(h, launch_feature_fuse(p, s)); }
+    { ProfScope ps(h, s, 3, (double)W * T * ((double)h->raw_total * 4 + (tc ? (double)h->D16 * 2 : (double)h->D * 4))); LAUNCH_TRY(h, launch_feature_fuse(p, s)); h->launches += feature_fuse_launches(p) - 1; }
     float* seq = seq_embed + w0 * kD;
     float* fr = frame_embeds ? frame_embeds + w0 * S * kD : nullptr;
     float* tk = tokens ? tokens + w0 * S * kD : nullptr;
