@@ -201,7 +201,15 @@ def main():
     dims_raw, dims_diff = pkg.dims_maps(False)
     sd = pkg.make_state_dict(dims_raw, dims_diff, seed=0)
     n_windows = args.videos * ((args.frames - CLIP_LEN) // STRIDE + 1 if args.frames >= CLIP_LEN else 1)
-    max_windows = args.max_windows or (min(n_windows, 12544) if args.precision == "fp16_tc" else min(n_windows, 2048))
+    if args.max_windows:
+        max_windows = args.max_windows
+    elif args.precision == "fp16_tc":
+        # windows per pass: a whole number of waves of the persistent tensor-core GEMM (74 CTA pairs x 256 rows = 592
+        # windows of 32 frames per wave), about 12.5k windows (8 GB of workspace) per pass
+        n_pass = -(-n_windows // 12800)
+        max_windows = min(n_windows, -(-(-(-n_windows // n_pass)) // 592) * 592)
+    else:
+        max_windows = min(n_windows, 2048)
     model = pkg.HumanActionScorer(dims_raw, dims_diff, precision=args.precision, max_windows=max_windows)
     model.load_state_dict(sd)
     model.to(dev).eval()

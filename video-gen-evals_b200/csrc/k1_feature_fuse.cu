@@ -251,6 +251,225 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Shared-memory staged variant for the tensor-core path (fp16 padded output only).
+// One CTA = one window x kS = 8 consecutive frames, one warp per frame:
+//   load    the kS+1 source rows of every modality land in shared memory first — the wide cosine rows by
+//           cp.async.bulk (one 16-byte-aligned row per copy, completion on an mbarrier), the small modalities by
+//           coalesced loads issued up front by all 256 threads — so a CTA has ~49 KB of reads in flight at once
+//           instead of a chain of dependent per-modality round trips;
+//   compute each warp builds its frame's [raw || diff] row (z-scored, fp16, pad columns zero) in shared memory;
+//   store   the kS output rows of a block are contiguous in feats16: ONE cp.async.bulk shared->global per CTA.
+constexpr int kS = 8;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, int in_floats_per_row, int smem_in_bytes) {
+  extern __shared__ __align__(128) unsigned char sm_raw[];
+  float* s_in = reinterpret_cast<float*>(sm_raw);                                   // [kS+1][in_floats_per_row]
+  __half* s_out = reinterpret_cast<__half*>(sm_raw + smem_in_bytes);               // [kS][D16]
+  float* s_inv = reinterpret_cast<float*>(sm_raw + smem_in_bytes + kS * p.D16 * 2); // [M][kS+1]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_inv + TAG_MAX_MODALITIES * (kS + 1) + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int blocks_per_win = (p.T + kS - 1) / kS;
+  const int64_t w = blockIdx.x / blocks_per_win;
+  const int t0 = (int)(blockIdx.x - w * blocks_per_win) * kS;
+  const int nf = min(kS, p.T - t0);
+  const int vid = p.win_video[w];
+  const int start = p.win_start[w];
+  const int64_t f0 = p.frame_offset[vid];
+  const int L = (int)(p.frame_offset[vid + 1] - f0);
+  auto row_of = [&](int t) -> int64_t { return f0 + src_frame(start, t < 0 ? 0 : t, L); };
+  const uint32_t bar = smem_addr(s_bar);
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the output tile (pad columns stay zero)
+  for (int i = tid; i < kS * p.D16 / 8; i += 256) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+
+  // ---- load phase
+  int col = 0;                                   // float offset of modality m inside a staged row
+  uint32_t tx = 0;
+#pragma unroll 1
+  for (int m = 0; m < p.M; ++m) {
+    const int dim = p.raw_dim[m];
+    if (p.kind[m] == TAG_KIND_COSINE) tx += (uint32_t)((nf + 1) * dim * 4);
+    col += (dim + 3) & ~3;
+  }
+  if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+  __syncthreads();
+  col = 0;
+#pragma unroll 1
+  for (int m = 0; m < p.M; ++m) {
+    const int dim = p.raw_dim[m];
+    const float* src = p.src[m];
+    if (p.kind[m] == TAG_KIND_COSINE) {
+      if (tid <= nf) {                           // one bulk copy per row (rows may repeat when the window is padded)
+        const float* g = src + row_of(t0 + tid - 1) * dim;
+        const uint32_t d = smem_addr(s_in + tid * in_floats_per_row + col);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(g), "r"((uint32_t)(dim * 4)), "r"(bar) : "memory");
+      }
+    } else {
+      for (int e = tid; e < (nf + 1) * dim; e += 256) {
+        const int r = e / dim, i = e - r * dim;
+        s_in[r * in_floats_per_row + col + i] = __ldg(src + row_of(t0 + r - 1) * dim + i);
+      }
+    }
+    col += (dim + 3) & ~3;
+  }
+  {  // wait for the bulk copies (bounded: a protocol bug must not hang the GPU)
+    uint32_t ok = 0;
+    const long long c0 = clock64();
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(0) : "memory");
+      if (!ok && clock64() - c0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+
+  // ---- row norms of the cosine modalities: warp f -> row f+1, warp 0 also row 0
+  col = 0;
+#pragma unroll 1
+  for (int m = 0; m < p.M; ++m) {
+    const int dim = p.raw_dim[m];
+    if (p.kind[m] == TAG_KIND_COSINE) {
+      for (int r = warp + 1; r >= 0; r -= (warp == 0 ? 1 : kS + 2)) {     // warp 0: rows 1 and 0; warp f: row f+1
+        if (r <= nf) {
+          const float* x = s_in + r * in_floats_per_row + col;
+          float ss = 0.f;
+          for (int i = 2 * lane; i < dim; i += 64) {
+            const float2 a = *reinterpret_cast<const float2*>(x + i);
+            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
+          }
+          ss = warp_sum(ss);
+          if (lane == 0) s_inv[m * (kS + 1) + r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        }
+      }
+    }
+    col += (dim + 3) & ~3;
+  }
+  __syncthreads();
+
+  // ---- compute phase: warp f builds output row f
+  const Norm nz{p.mean, p.stdv};
+  if (warp < nf) {
+    const int f = warp, t = t0 + f;
+    __half* o16 = s_out + f * p.D16;
+    col = 0;
+#pragma unroll 1
+    for (int m = 0; m < p.M; ++m) {
+      const int dim = p.raw_dim[m];
+      const float* xc = s_in + (f + 1) * in_floats_per_row + col;
+      const float* xp = s_in + f * in_floats_per_row + col;
+      const int ro = p.raw_off[m], dofs = p.diff_off[m];
+      const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
+      const int kind = p.kind[m];
+      const bool has_diff = p.diff_dim[m] > 0;
+      col += (dim + 3) & ~3;
+      if (kind == TAG_KIND_COSINE) {
+        const float inv = s_inv[m * (kS + 1) + f + 1], invp = has_diff ? s_inv[m * (kS + 1) + f] : 0.f;
+#pragma unroll 4
+        for (int i = 2 * lane; i < dim; i += 64) {
+          const float2 a = *reinterpret_cast<const float2*>(xc + i);
+          *reinterpret_cast<__half2*>(o16 + ro16 + i) = __floats2half2_rn(nz(a.x, ro + i), nz(a.y, ro + i + 1));
+          if (has_diff) {
+            const float2 b = *reinterpret_cast<const float2*>(xp + i);
+            *reinterpret_cast<__half2*>(o16 + do16 + i) =
+                __floats2half2_rn(nz(a.x * inv - b.x * invp, dofs + i), nz(a.y * inv - b.y * invp, dofs + i + 1));
+          }
+        }
+      } else if (kind == TAG_KIND_ROTMAT) {
+        for (int i = lane; i < dim; i += 32) o16[ro16 + i] = __float2half_rn(nz(xc[i], ro + i));
+        const int J = dim / 9;
+        if (has_diff) {
+          for (int jn = lane; jn < J; jn += 32) {
+            float R[9], Q[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { R[k] = xc[jn * 9 + k]; Q[k] = xp[jn * 9 + k]; }
+            float E[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
+            float tr = E[0] + E[4] + E[8];
+            tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
+            const float c = (tr - 1.f) / 2.f;
+            const float theta = acosf(c);
+            const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
+            const float k = theta / den;
+            const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) o16[do16 + jn * 3 + q] = __float2half_rn(nz(wv[q], dofs + jn * 3 + q));
+          }
+        }
+      } else if (kind == TAG_KIND_PLAIN) {
+        for (int i = lane; i < dim; i += 32) {
+          const float x = xc[i];
+          o16[ro16 + i] = __float2half_rn(nz(x, ro + i));
+          if (has_diff) o16[do16 + i] = __float2half_rn(nz(x - xp[i], dofs + i));
+        }
+      } else {  // TAG_KIND_PROCRUSTES
+        for (int i = lane; i < dim; i += 32) o16[ro16 + i] = __float2half_rn(nz(xc[i], ro + i));
+        if (has_diff) {
+          const int K = dim / 2;
+          const int k0 = lane, k1 = lane + 32;
+          const bool a0 = k0 < K, a1 = k1 < K;
+          auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
+            x0 = a0 ? x[2 * k0] : 0.f; y0 = a0 ? x[2 * k0 + 1] : 0.f;
+            x1 = a1 ? x[2 * k1] : 0.f; y1 = a1 ? x[2 * k1 + 1] : 0.f;
+            const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
+            x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
+            x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
+            const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
+            x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
+          };
+          float x0, y0, x1, y1, px0, py0, px1, py1;
+          load_norm(xc, x0, y0, x1, y1);
+          load_norm(xp, px0, py0, px1, py1);
+          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+          if (t > 0) {
+            const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
+            const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
+            if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+            const float ry = h10 - h01, rx = h00 + h11;
+            const float rr = ry * ry + rx * rx;
+            const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
+            const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
+            d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
+            d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
+          }
+          if (a0) {
+            o16[do16 + 2 * k0] = __float2half_rn(nz(d00, dofs + 2 * k0));
+            o16[do16 + 2 * k0 + 1] = __float2half_rn(nz(d01, dofs + 2 * k0 + 1));
+          }
+          if (a1) {
+            o16[do16 + 2 * k1] = __float2half_rn(nz(d10, dofs + 2 * k1));
+            o16[do16 + 2 * k1 + 1] = __float2half_rn(nz(d11, dofs + 2 * k1 + 1));
+          }
+        }
+      }
+    }
+  }
+  // ---- store phase: the block's rows are contiguous in feats16
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    __half* g = p.feats16 + ((int64_t)w * p.T + t0) * p.D16;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(g), "r"(smem_addr(s_out)), "r"((uint32_t)(nf * p.D16 * 2)) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* scale, float* shift, int D, cudaStream_t s) {
@@ -260,6 +479,29 @@ cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* sca
 
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
   if (p.n_windows <= 0) return cudaSuccess;
+  if (p.feats == nullptr && p.feats16 != nullptr) {
+    // staged (bulk-copy) kernel for the tensor-core path, when the rows are 16-byte friendly and the tile fits in smem
+    bool ok = true;
+    int in_floats = 0;
+    for (int m = 0; m < p.M; ++m) {
+      if (p.kind[m] == TAG_KIND_COSINE && (p.raw_dim[m] % 4) != 0) ok = false;
+      if (reinterpret_cast<uintptr_t>(p.src[m]) & 15) ok = false;
+      in_floats += (p.raw_dim[m] + 3) & ~3;
+    }
+    const int smem_in = ((kS + 1) * in_floats * 4 + 127) & ~127;
+    const int smem_total = smem_in + kS * p.D16 * 2 + (TAG_MAX_MODALITIES * (kS + 1) + 2) * 4 + 16;
+    if (ok && smem_total <= 227 * 1024 && (reinterpret_cast<uintptr_t>(p.feats16) & 15) == 0) {
+      static int configured = 0;
+      if (configured < smem_total) {
+        cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+        if (e != cudaSuccess) return e;
+        configured = smem_total;
+      }
+      const int64_t blocks = p.n_windows * ((p.T + kS - 1) / kS);
+      k_feature_fuse_staged<<<(unsigned)blocks, 256, smem_total, s>>>(p, in_floats, smem_in);
+      return cudaGetLastError();
+    }
+  }
   bool any_cos = false, any_small = false;
   for (int m = 0; m < p.M; ++m) { if (p.kind[m] == TAG_KIND_COSINE) any_cos = true; else any_small = true; }
   auto grid_for = [&](int kf) {

@@ -26,8 +26,10 @@ struct FuseParams {
 };
 cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* scale, float* shift, int D, cudaStream_t s);
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s);
-// kernels launched by launch_feature_fuse (one for the cosine modalities, one for the rest)
+// kernels launched by launch_feature_fuse: the staged kernel (fp16-only output) is one launch; the generic path is one
+// for the cosine modalities plus one for the rest
 inline int feature_fuse_launches(const FuseParams& p) {
+  if (p.feats == nullptr && p.feats16 != nullptr) return 1;
   bool c = false, o = false;
   for (int m = 0; m < p.M; ++m) { if (p.kind[m] == TAG_KIND_COSINE) c = true; else o = true; }
   return (c ? 1 : 0) + (o ? 1 : 0);
