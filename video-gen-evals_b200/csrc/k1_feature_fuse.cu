@@ -357,104 +357,134 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   }
   __syncthreads();
 
-  // ---- compute phase: warp f builds output row f
+  // ---- compute phase, item-parallel over the whole CTA (no warp-serial chains): a thread owns a column (pair) for
+  // all nf frames, so its two z-score table entries are loaded once and stay in registers; rotation joints and plain
+  // differences are spread as (frame, item) pairs; only the keypoint alignment is a warp-per-frame reduction.
   const Norm nz{p.mean, p.stdv};
-  if (warp < nf) {
-    const int f = warp, t = t0 + f;
-    __half* o16 = s_out + f * p.D16;
-    col = 0;
+  col = 0;
 #pragma unroll 1
-    for (int m = 0; m < p.M; ++m) {
-      const int dim = p.raw_dim[m];
-      const float* xc = s_in + (f + 1) * in_floats_per_row + col;
-      const float* xp = s_in + f * in_floats_per_row + col;
-      const int ro = p.raw_off[m], dofs = p.diff_off[m];
-      const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
-      const int kind = p.kind[m];
-      const bool has_diff = p.diff_dim[m] > 0;
-      col += (dim + 3) & ~3;
-      if (kind == TAG_KIND_COSINE) {
-        const float inv = s_inv[m * (kS + 1) + f + 1], invp = has_diff ? s_inv[m * (kS + 1) + f] : 0.f;
-#pragma unroll 4
-        for (int i = 2 * lane; i < dim; i += 64) {
-          const float2 a = *reinterpret_cast<const float2*>(xc + i);
-          *reinterpret_cast<__half2*>(o16 + ro16 + i) = __floats2half2_rn(nz(a.x, ro + i), nz(a.y, ro + i + 1));
+  for (int m = 0; m < p.M; ++m) {
+    const int dim = p.raw_dim[m];
+    const float* xin = s_in + col;                       // row r of this modality: xin + r * in_floats_per_row
+    const int ro = p.raw_off[m], dofs = p.diff_off[m];
+    const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
+    const int kind = p.kind[m];
+    const bool has_diff = p.diff_dim[m] > 0;
+    col += (dim + 3) & ~3;
+
+    if (kind == TAG_KIND_COSINE) {
+      const float* invm = s_inv + m * (kS + 1);
+      for (int i = 2 * tid; i < dim; i += 512) {
+        float2 sr = make_float2(1.f, 1.f), hr = make_float2(0.f, 0.f), sd = sr, hd = hr;
+        if (nz.scale != nullptr) {
+          sr = *reinterpret_cast<const float2*>(nz.scale + ro + i);    // ro, dofs even on this path (checked on the host)
+          hr = *reinterpret_cast<const float2*>(nz.shift + ro + i);
           if (has_diff) {
-            const float2 b = *reinterpret_cast<const float2*>(xp + i);
-            *reinterpret_cast<__half2*>(o16 + do16 + i) =
-                __floats2half2_rn(nz(a.x * inv - b.x * invp, dofs + i), nz(a.y * inv - b.y * invp, dofs + i + 1));
+            sd = *reinterpret_cast<const float2*>(nz.scale + dofs + i);
+            hd = *reinterpret_cast<const float2*>(nz.shift + dofs + i);
           }
         }
-      } else if (kind == TAG_KIND_ROTMAT) {
-        for (int i = lane; i < dim; i += 32) o16[ro16 + i] = __float2half_rn(nz(xc[i], ro + i));
-        const int J = dim / 9;
-        if (has_diff) {
-          for (int jn = lane; jn < J; jn += 32) {
-            float R[9], Q[9];
+        float2 prev = *reinterpret_cast<const float2*>(xin + i);
+        prev.x *= invm[0]; prev.y *= invm[0];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { R[k] = xc[jn * 9 + k]; Q[k] = xp[jn * 9 + k]; }
-            float E[9];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-                E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
-            float tr = E[0] + E[4] + E[8];
-            tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
-            const float c = (tr - 1.f) / 2.f;
-            const float theta = acosf(c);
-            const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
-            const float k = theta / den;
-            const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
-#pragma unroll
-            for (int q = 0; q < 3; ++q) o16[do16 + jn * 3 + q] = __float2half_rn(nz(wv[q], dofs + jn * 3 + q));
+        for (int f = 0; f < kS; ++f) {
+          if (f < nf) {
+            const float2 a = *reinterpret_cast<const float2*>(xin + (f + 1) * in_floats_per_row + i);
+            __half* o16 = s_out + f * p.D16;
+            *reinterpret_cast<__half2*>(o16 + ro16 + i) = __floats2half2_rn(fmaf(a.x, sr.x, hr.x), fmaf(a.y, sr.y, hr.y));
+            if (has_diff) {
+              const float2 cur = make_float2(a.x * invm[f + 1], a.y * invm[f + 1]);
+              *reinterpret_cast<__half2*>(o16 + do16 + i) =
+                  __floats2half2_rn(fmaf(cur.x - prev.x, sd.x, hd.x), fmaf(cur.y - prev.y, sd.y, hd.y));
+              prev = cur;
+            }
           }
         }
-      } else if (kind == TAG_KIND_PLAIN) {
-        for (int i = lane; i < dim; i += 32) {
-          const float x = xc[i];
-          o16[ro16 + i] = __float2half_rn(nz(x, ro + i));
-          if (has_diff) o16[do16 + i] = __float2half_rn(nz(x - xp[i], dofs + i));
-        }
-      } else {  // TAG_KIND_PROCRUSTES
-        for (int i = lane; i < dim; i += 32) o16[ro16 + i] = __float2half_rn(nz(xc[i], ro + i));
-        if (has_diff) {
-          const int K = dim / 2;
-          const int k0 = lane, k1 = lane + 32;
-          const bool a0 = k0 < K, a1 = k1 < K;
-          auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
-            x0 = a0 ? x[2 * k0] : 0.f; y0 = a0 ? x[2 * k0 + 1] : 0.f;
-            x1 = a1 ? x[2 * k1] : 0.f; y1 = a1 ? x[2 * k1 + 1] : 0.f;
-            const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
-            x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
-            x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
-            const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
-            x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
-          };
-          float x0, y0, x1, y1, px0, py0, px1, py1;
-          load_norm(xc, x0, y0, x1, y1);
-          load_norm(xp, px0, py0, px1, py1);
-          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-          if (t > 0) {
-            const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
-            const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
-            if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
-            const float ry = h10 - h01, rx = h00 + h11;
-            const float rr = ry * ry + rx * rx;
-            const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
-            const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
-            d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
-            d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
-          }
-          if (a0) {
-            o16[do16 + 2 * k0] = __float2half_rn(nz(d00, dofs + 2 * k0));
-            o16[do16 + 2 * k0 + 1] = __float2half_rn(nz(d01, dofs + 2 * k0 + 1));
-          }
-          if (a1) {
-            o16[do16 + 2 * k1] = __float2half_rn(nz(d10, dofs + 2 * k1));
-            o16[do16 + 2 * k1 + 1] = __float2half_rn(nz(d11, dofs + 2 * k1 + 1));
-          }
-        }
+      }
+      continue;
+    }
+    // raw columns of the small modalities: one column per thread, all frames
+    for (int i = tid; i < dim; i += 256) {
+      const float sc = nz.scale ? __ldg(nz.scale + ro + i) : 1.f, sh = nz.scale ? __ldg(nz.shift + ro + i) : 0.f;
+#pragma unroll
+      for (int f = 0; f < kS; ++f)
+        if (f < nf) s_out[f * p.D16 + ro16 + i] = __float2half_rn(fmaf(xin[(f + 1) * in_floats_per_row + i], sc, sh));
+    }
+    if (!has_diff) continue;
+    if (kind == TAG_KIND_ROTMAT) {
+      const int J = dim / 9;
+      for (int e = tid; e < nf * J; e += 256) {           // (frame, joint) pairs
+        const int f = e / J, jn = e - f * J;
+        const float* xc = xin + (f + 1) * in_floats_per_row + jn * 9;
+        const float* xp = xin + f * in_floats_per_row + jn * 9;
+        float R[9], Q[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { R[k] = xc[k]; Q[k] = xp[k]; }
+        // Rrel = Q^T R  (utils.py:172), entries [i][j] = sum_k Q[k][i] R[k][j]
+        float E[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
+        float tr = E[0] + E[4] + E[8];
+        tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
+        const float c = (tr - 1.f) / 2.f;
+        const float theta = acosf(c);
+        const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
+        const float k = theta / den;
+        const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s_out[f * p.D16 + do16 + jn * 3 + q] = __float2half_rn(nz(wv[q], dofs + jn * 3 + q));
+      }
+    } else if (kind == TAG_KIND_PLAIN) {
+      for (int e = tid; e < nf * dim; e += 256) {         // (frame, column) pairs
+        const int f = e / dim, i = e - f * dim;
+        const float d = xin[(f + 1) * in_floats_per_row + i] - xin[f * in_floats_per_row + i];
+        s_out[f * p.D16 + do16 + i] = __float2half_rn(nz(d, dofs + i));
+      }
+    } else if (warp < nf) {  // TAG_KIND_PROCRUSTES: warp f aligns frame t0+f-1 -> t0+f
+      const int f = warp, t = t0 + f;
+      const float* xc = xin + (f + 1) * in_floats_per_row;
+      const float* xp = xin + f * in_floats_per_row;
+      __half* o16 = s_out + f * p.D16;
+      const int K = dim / 2;
+      const int k0 = lane, k1 = lane + 32;
+      const bool a0 = k0 < K, a1 = k1 < K;
+      // centre + Frobenius-normalise one frame's points (utils.py:192-196)
+      auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
+        x0 = a0 ? x[2 * k0] : 0.f; y0 = a0 ? x[2 * k0 + 1] : 0.f;
+        x1 = a1 ? x[2 * k1] : 0.f; y1 = a1 ? x[2 * k1 + 1] : 0.f;
+        const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
+        x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
+        x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
+        const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
+        x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
+      };
+      float x0, y0, x1, y1, px0, py0, px1, py1;
+      load_norm(xc, x0, y0, x1, y1);
+      load_norm(xp, px0, py0, px1, py1);
+      float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+      if (t > 0) {
+        // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
+        const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
+        const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
+        if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+        // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
+        const float ry = h10 - h01, rx = h00 + h11;
+        const float rr = ry * ry + rx * rx;
+        const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
+        const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
+        d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
+        d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
+      }
+      if (a0) {
+        o16[do16 + 2 * k0] = __float2half_rn(nz(d00, dofs + 2 * k0));
+        o16[do16 + 2 * k0 + 1] = __float2half_rn(nz(d01, dofs + 2 * k0 + 1));
+      }
+      if (a1) {
+        o16[do16 + 2 * k1] = __float2half_rn(nz(d10, dofs + 2 * k1));
+        o16[do16 + 2 * k1 + 1] = __float2half_rn(nz(d11, dofs + 2 * k1 + 1));
       }
     }
   }
@@ -484,7 +514,7 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
     bool ok = true;
     int in_floats = 0;
     for (int m = 0; m < p.M; ++m) {
-      if (p.kind[m] == TAG_KIND_COSINE && (p.raw_dim[m] % 4) != 0) ok = false;
+      if (p.kind[m] == TAG_KIND_COSINE && ((p.raw_dim[m] % 4) != 0 || (p.raw_off[m] & 1) || (p.diff_off[m] & 1))) ok = false;
       if (reinterpret_cast<uintptr_t>(p.src[m]) & 15) ok = false;
       in_floats += (p.raw_dim[m] + 3) & ~3;
     }
