@@ -316,9 +316,23 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
                      ::"r"(d), "l"(g), "r"((uint32_t)(dim * 4)), "r"(bar) : "memory");
       }
     } else {
-      for (int e = tid; e < (nf + 1) * dim; e += 256) {
-        const int r = e / dim, i = e - r * dim;
-        s_in[r * in_floats_per_row + col + i] = __ldg(src + row_of(t0 + r - 1) * dim + i);
+      // all loads of a batch are issued before the first store (the profile of an earlier version showed this loop
+      // as a chain of one DRAM round trip per iteration)
+      const int n = (nf + 1) * dim;
+      for (int e0 = 0; e0 < n; e0 += 8 * 256) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = e0 + k * 256 + tid;
+          const int r = e / dim, i = e - r * dim;
+          v[k] = e < n ? __ldg(src + row_of(t0 + r - 1) * dim + i) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int e = e0 + k * 256 + tid;
+          const int r = e / dim, i = e - r * dim;
+          if (e < n) s_in[r * in_floats_per_row + col + i] = v[k];
+        }
       }
     }
     col += (dim + 3) & ~3;
