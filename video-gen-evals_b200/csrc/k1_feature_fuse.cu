@@ -316,23 +316,14 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
                      ::"r"(d), "l"(g), "r"((uint32_t)(dim * 4)), "r"(bar) : "memory");
       }
     } else {
-      // all loads of a batch are issued before the first store (the profile of an earlier version showed this loop
-      // as a chain of one DRAM round trip per iteration)
-      const int n = (nf + 1) * dim;
-      for (int e0 = 0; e0 < n; e0 += 8 * 256) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int e = e0 + k * 256 + tid;
-          const int r = e / dim, i = e - r * dim;
-          v[k] = e < n ? __ldg(src + row_of(t0 + r - 1) * dim + i) : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int e = e0 + k * 256 + tid;
-          const int r = e / dim, i = e - r * dim;
-          if (e < n) s_in[r * in_floats_per_row + col + i] = v[k];
-        }
+      // warp r stages row r (warp 0 also the last row): no per-element index arithmetic, and with the unroll all of a
+      // lane's loads are in flight before its first store (an earlier version with a flat element loop spent most of
+      // its instructions on integer divisions and one DRAM round trip per iteration)
+      for (int r = warp; r <= nf; r += 8) {
+        const float* g = src + row_of(t0 + r - 1) * dim;
+        float* d = s_in + r * in_floats_per_row + col;
+#pragma unroll 8
+        for (int i = lane; i < dim; i += 32) d[i] = __ldg(g + i);
       }
     }
     col += (dim + 3) & ~3;
@@ -427,8 +418,8 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
     if (!has_diff) continue;
     if (kind == TAG_KIND_ROTMAT) {
       const int J = dim / 9;
-      for (int e = tid; e < nf * J; e += 256) {           // (frame, joint) pairs
-        const int f = e / J, jn = e - f * J;
+      for (int jn = lane; warp < nf && jn < J; jn += 32) {     // warp = frame, lane = joint
+        const int f = warp;
         const float* xc = xin + (f + 1) * in_floats_per_row + jn * 9;
         const float* xp = xin + f * in_floats_per_row + jn * 9;
         float R[9], Q[9];
@@ -452,8 +443,8 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
         for (int q = 0; q < 3; ++q) s_out[f * p.D16 + do16 + jn * 3 + q] = __float2half_rn(nz(wv[q], dofs + jn * 3 + q));
       }
     } else if (kind == TAG_KIND_PLAIN) {
-      for (int e = tid; e < nf * dim; e += 256) {         // (frame, column) pairs
-        const int f = e / dim, i = e - f * dim;
+      for (int i = lane; warp < nf && i < dim; i += 32) {      // warp = frame, lane = column
+        const int f = warp;
         const float d = xin[(f + 1) * in_floats_per_row + i] - xin[f * in_floats_per_row + i];
         s_out[f * p.D16 + do16 + i] = __float2half_rn(nz(d, dofs + i));
       }
