@@ -261,10 +261,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
 //           instead of a chain of dependent per-modality round trips;
 //   compute each warp builds its frame's [raw || diff] row (z-scored, fp16, pad columns zero) in shared memory;
 //   store   the kS output rows of a block are contiguous in feats16: ONE cp.async.bulk shared->global per CTA.
-constexpr int kS = 8;
+// kS = 4 frames per CTA: 5 input rows (27 KB) + 4 output rows (23 KB) -> 4 CTAs (32 warps) per SM, so one CTA's load
+// phase overlaps the others' compute/store phases (kS = 8 left only 2 CTAs per SM and measured slower).
+constexpr int kStagedFrames = 4;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <int kS>
 __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, int in_floats_per_row, int smem_in_bytes) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
   float* s_in = reinterpret_cast<float*>(sm_raw);                                   // [kS+1][in_floats_per_row]
@@ -351,14 +354,14 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   }
   __syncthreads();
 
-  // ---- row norms of the cosine modalities: warp f -> row f+1, warp 0 also row 0
+  // ---- row norms of the cosine modalities: one row per warp
   col = 0;
 #pragma unroll 1
   for (int m = 0; m < p.M; ++m) {
     const int dim = p.raw_dim[m];
     if (p.kind[m] == TAG_KIND_COSINE) {
-      for (int r = warp + 1; r >= 0; r -= (warp == 0 ? 1 : kS + 2)) {     // warp 0: rows 1 and 0; warp f: row f+1
-        if (r <= nf) {
+      for (int r = warp; r <= nf; r += 8) {                               // one row per warp (two for warp 0 when kS = 8)
+        {
           const float* x = s_in + r * in_floats_per_row + col;
           float ss = 0.f;
           for (int i = 2 * lane; i < dim; i += 64) {
@@ -535,17 +538,18 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
       if (reinterpret_cast<uintptr_t>(p.src[m]) & 15) ok = false;
       in_floats += (p.raw_dim[m] + 3) & ~3;
     }
+    constexpr int kS = kStagedFrames;
     const int smem_in = ((kS + 1) * in_floats * 4 + 127) & ~127;
     const int smem_total = smem_in + kS * p.D16 * 2 + (TAG_MAX_MODALITIES * (kS + 1) + 2) * 4 + 16;
     if (ok && smem_total <= 227 * 1024 && (reinterpret_cast<uintptr_t>(p.feats16) & 15) == 0) {
       static int configured = 0;
       if (configured < smem_total) {
-        cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+        cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
         if (e != cudaSuccess) return e;
         configured = smem_total;
       }
       const int64_t blocks = p.n_windows * ((p.T + kS - 1) / kS);
-      k_feature_fuse_staged<<<(unsigned)blocks, 256, smem_total, s>>>(p, in_floats, smem_in);
+      k_feature_fuse_staged<kS><<<(unsigned)blocks, 256, smem_total, s>>>(p, in_floats, smem_in);
       return cudaGetLastError();
     }
   }
