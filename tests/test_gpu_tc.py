@@ -177,6 +177,29 @@ def test_fused_pipeline_tc_scores():
     assert int(scorer.last_flags.item()) == 0
 
 
+def test_score_stream_matches_resident_scores():
+    """score_stream over several host batches of different sizes (prefetch across batch boundaries) returns, batch by
+    batch and in order, exactly what TagScorer.score returns for the same videos resident on the device."""
+    g = golden_case("m5_t32")
+    model = _model(g, "fp16_tc", max_windows=16)
+    scorer = tb.TagScorer(model, g.stats(), clip_len=g.clip_len, stride=g.stride, device=DEV)
+    cen = torch.from_numpy(g.npz["centroids"]).to(DEV)
+    V = g.gen.n_videos
+    cuts = [(0, V), (0, max(1, V // 3)), (max(1, V // 3), V), (0, 1), (0, V)]
+    host = [g.gen.slice(a, b).pin() for a, b in cuts]
+    want = []
+    for hb in host:
+        a, t = scorer.score(scorer.to_device(hb.to(DEV)), cen)
+        want.append((a.cpu(), t.cpu()))
+    for pieces, prefetch in ((1, 0), (2, 2), (3, 1), (7, 4)):
+        got = list(scorer.score_stream(iter(host), cen, pieces=pieces, prefetch=prefetch))
+        assert len(got) == len(host)
+        for (ga, gt), (wa, wt) in zip(got, want):
+            assert ga.shape == wa.shape
+            assert torch.allclose(ga, wa, rtol=0, atol=2e-6, equal_nan=True) and torch.allclose(gt, wt, rtol=0, atol=2e-6)
+    assert list(scorer.score_stream(iter([]), cen)) == []
+
+
 @pytest.mark.parametrize("M,K", [(330, 256), (128 * 9 + 5, 1024), (64, 256)])
 def test_gemm_tc_fused_layernorm(M, K):
     """out-proj / FFN2 form of the post-norm transformer layer (model.py:145): X <- LayerNorm(A W^T + b + X), fp32 stream

@@ -14,6 +14,8 @@
 // HBM-bound: per (window, frame) reads sum(raw_dims)*4 B and writes D*4 B (fp32 feats) and/or D16*2 B
 // (padded fp16 operand for the tensor-core encoder). One warp per (window, 8 consecutive frames); overlapping
 // windows re-read source frames through L2, so DRAM sees each source frame about once or twice per batch.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -268,7 +270,7 @@ constexpr int kStagedFrames = 4;
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int kS>
-__global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, int in_floats_per_row, int smem_in_bytes) {
+__global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, int in_floats_per_row, int smem_in_bytes, int dbg) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
   float* s_in = reinterpret_cast<float*>(sm_raw);                                   // [kS+1][in_floats_per_row]
   __half* s_out = reinterpret_cast<__half*>(sm_raw + smem_in_bytes);               // [kS][D16]
@@ -304,6 +306,7 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
     if (p.kind[m] == TAG_KIND_COSINE) tx += (uint32_t)((nf + 1) * dim * 4);
     col += (dim + 3) & ~3;
   }
+  if (dbg & 4) tx = 0;                           // experiment: no loads
   if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
   __syncthreads();
   col = 0;
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   for (int m = 0; m < p.M; ++m) {
     const int dim = p.raw_dim[m];
     const float* src = p.src[m];
+    if (dbg & 4) { col += (dim + 3) & ~3; continue; }
     if (p.kind[m] == TAG_KIND_COSINE) {
       if (tid <= nf) {                           // one bulk copy per row (rows may repeat when the window is padded)
         const float* g = src + row_of(t0 + tid - 1) * dim;
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   // ---- row norms of the cosine modalities: one row per warp
   col = 0;
 #pragma unroll 1
-  for (int m = 0; m < p.M; ++m) {
+  for (int m = 0; m < ((dbg & 1) ? 0 : p.M); ++m) {
     const int dim = p.raw_dim[m];
     if (p.kind[m] == TAG_KIND_COSINE) {
       for (int r = warp; r <= nf; r += 8) {                               // one row per warp (two for warp 0 when kS = 8)
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   const Norm nz{p.mean, p.stdv};
   col = 0;
 #pragma unroll 1
-  for (int m = 0; m < p.M; ++m) {
+  for (int m = 0; m < ((dbg & 1) ? 0 : p.M); ++m) {
     const int dim = p.raw_dim[m];
     const float* xin = s_in + col;                       // row r of this modality: xin + r * in_floats_per_row
     const int ro = p.raw_off[m], dofs = p.diff_off[m];
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   // ---- store phase: the block's rows are contiguous in feats16
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && !(dbg & 2)) {
     __half* g = p.feats16 + ((int64_t)w * p.T + t0) * p.D16;
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(g), "r"(smem_addr(s_out)), "r"((uint32_t)(nf * p.D16 * 2)) : "memory");
@@ -549,7 +553,9 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
         configured = smem_total;
       }
       const int64_t blocks = p.n_windows * ((p.T + kS - 1) / kS);
-      k_feature_fuse_staged<kS><<<(unsigned)blocks, 256, smem_total, s>>>(p, in_floats, smem_in);
+      static int dbg = -1;
+      if (dbg < 0) { const char* e = getenv("TAG_K1_DEBUG"); dbg = e ? atoi(e) : 0; }   // bottleneck experiments only
+      k_feature_fuse_staged<kS><<<(unsigned)blocks, 256, smem_total, s>>>(p, in_floats, smem_in, dbg);
       return cudaGetLastError();
     }
   }

@@ -121,44 +121,87 @@ class TagScorer:
         self.last_flags = enc["flags"]
         return ac, tc
 
-    def score_host(self, vb_host: VideoBatch, centroids: torch.Tensor, pieces: int = 4) -> Tuple[torch.Tensor, torch.Tensor]:
-        """End-to-end call with HOST buffers: H2D of every input array, score, D2H of the per-video
-        results. This is the `e2e` leg of bench.py. Returns CPU tensors (ac [V], tc [V]).
+    def score_stream(self, batches, centroids: torch.Tensor, pieces: int = 2, prefetch: int = 2):
+        """Streaming end-to-end call: `batches` is an iterable of HOST (ideally pinned) VideoBatch objects; yields
+        one `(ac [V], tc [V])` pair of CPU tensors per batch, in order. This is the `e2e` leg of bench.py.
 
-        The batch is cut into `pieces` contiguous blocks of videos; block i+1 is copied on a side stream while
-        block i is being scored (the inputs are 350 KB per video, the results 8 B), so with pinned host memory the
-        PCIe time hides behind the encoder instead of adding to it."""
-        V = vb_host.n_videos
-        pieces = max(1, min(int(pieces), V))
+        Every batch is cut into `pieces` contiguous blocks of videos. Blocks are copied host->device on a side stream
+        up to `prefetch` blocks ahead of the block being scored (across batch boundaries), and the 8 B/video results
+        go back through a pinned buffer one batch behind the compute, so in steady state the PCIe time (350 KB per
+        video) hides behind the encoder. At most prefetch+2 blocks of inputs are alive on the device."""
+        from collections import deque
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
         cs.wait_stream(main)
-        ac = torch.empty(V, device=dev, dtype=torch.float32)
-        tc = torch.empty(V, device=dev, dtype=torch.float32)
-        bounds = [shard_range(V, i, pieces) for i in range(pieces)]
-        staged = []
-        for lo, hi in bounds:                      # enqueue all copies up front on the copy stream, in order
+
+        def jobs():
+            for vb in batches:
+                n = max(1, min(int(pieces), vb.n_videos))
+                for i in range(n):
+                    lo, hi = shard_range(vb.n_videos, i, n)
+                    yield vb, lo, hi, i == n - 1
+
+        it = jobs()
+        staged, done = deque(), []
+
+        def stage():
+            job = next(it, None)
+            if job is None:
+                return
+            vb, lo, hi, last = job
+            j = len(done) + len(staged)                       # index of this block in the stream
+            if j - prefetch - 2 >= 0:
+                cs.wait_event(done[j - prefetch - 2])         # bound the device copies that are alive
             with torch.cuda.stream(cs):
-                piece = vb_host.slice(lo, hi).to(dev)
+                piece = vb.slice(lo, hi).to(dev)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            staged.append((piece, ev))
-        flags = 0
-        for (lo, hi), (piece, ev) in zip(bounds, staged):
+            staged.append((vb, lo, hi, last, piece, ev))
+
+        def finish(p):
+            ev, host, flags = p
+            ev.synchronize()
+            self.last_flags = flags
+            return host[0], host[1]
+
+        for _ in range(prefetch + 1):
+            stage()
+        pending, out, flags = None, None, None
+        while staged:
+            vb, lo, hi, last, piece, ev = staged.popleft()
             main.wait_event(ev)
             for t in (piece.pose, piece.gori, piece.betas, piece.vit, piece.kp, piece.clip, piece.dino):
                 if t is not None:
                     t.record_stream(main)
+            if lo == 0:
+                out = torch.empty(2, vb.n_videos, device=dev, dtype=torch.float32)
+                flags = None
             a, t_ = self.score(DeviceVideos(piece, self.model.modalities, dev), centroids)
-            ac[lo:hi].copy_(a)
-            tc[lo:hi].copy_(t_)
-            flags = self.last_flags if isinstance(flags, int) else flags + self.last_flags
-        self.last_flags = flags
-        out = torch.stack([ac, tc], 0).cpu()
-        return out[0], out[1]
+            out[0, lo:hi].copy_(a)
+            out[1, lo:hi].copy_(t_)
+            flags = self.last_flags if flags is None else flags + self.last_flags
+            d = torch.cuda.Event()
+            d.record(main)
+            done.append(d)
+            stage()                                           # keep the copy window full
+            if last:
+                host = torch.empty(2, vb.n_videos, dtype=torch.float32, pin_memory=True)
+                host.copy_(out, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(main)
+                if pending is not None:
+                    yield finish(pending)                     # one batch behind: the GPU never waits for the host
+                pending = (e, host, flags)
+        if pending is not None:
+            yield finish(pending)
+
+    def score_host(self, vb_host: VideoBatch, centroids: torch.Tensor, pieces: int = 4) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End-to-end call with HOST buffers for one batch: H2D of every input array, score, D2H of the per-video
+        results (`score_stream` over a single batch). Returns CPU tensors (ac [V], tc [V])."""
+        return next(iter(self.score_stream([vb_host], centroids, pieces=pieces, prefetch=pieces)))
 
     def scores_dict(self, vb: VideoBatch, ac: torch.Tensor, tc: torch.Tensor) -> Dict[str, Dict[str, float]]:
         """{video_id: {"ac","tc"}} as eval.py:439-447 (a key is absent when the reference would skip it)."""
