@@ -177,6 +177,21 @@ def test_fused_pipeline_tc_scores():
     assert int(scorer.last_flags.item()) == 0
 
 
+def test_gemm_tc_halo_mode_in_subprocess():
+    """The optional halo-tile conv path (TAG_TC_HALO=2: one activation load per 64-channel chunk, taps as shifted
+    descriptor views, (t, window)-ordered accumulator rows) must give the same results as the default path: re-run the
+    conv GEMM and fused-GroupNorm cases of this file in a child process with the switch set."""
+    import os, subprocess, sys
+    if os.environ.get("TAG_TC_HALO"):
+        pytest.skip("already inside the halo-mode child")
+    env = dict(os.environ, TAG_TC_HALO="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "(test_gemm_tc and _t5d) or fused_groupnorm"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout
+
+
 def test_score_stream_matches_resident_scores():
     """score_stream over several host batches of different sizes (prefetch across batch boundaries) returns, batch by
     batch and in order, exactly what TagScorer.score returns for the same videos resident on the device."""

@@ -10,6 +10,17 @@
 // coordinate is shifted by (j-2)*dil — TMA's out-of-bounds zero fill IS the conv's zero padding — all
 // accumulating into one TMEM tile.
 //
+// Halo mode (TAG_TC_HALO=1|2, off by default): the five shifted loads re-read every activation row five times from
+// L2 (~1 GB of the ~2 GB L2->SM traffic of a conv launch). In halo mode the producer loads each 64-channel chunk ONCE
+// as a box (channel, window, t) = (64, NW, T' + 4*dil) starting at t = -2*dil: rows land in shared memory ordered
+// (t, window) — row = (t + 2*dil) * NW + w — with TMA's zero fill supplying the conv padding rows, and tap j is the
+// same tile read through a descriptor whose start address is advanced by j*dil*NW rows. The accumulator rows are then
+// (t, window)-ordered too; the epilogue maps them back to [window][t] rows when it addresses global memory.
+// Measured on B200 (same box, A/B): bit-identical results, 5x less activation traffic from L2, but 2-3 % SLOWER
+// (conv share of a bench step 212-215 ms vs 206-210 ms): the kernel is bound by the board power cap (SM clock
+// 1.55-1.75 GHz under sw_power_cap), not by L2->SM bandwidth, and the deeper {A,B} ring hides latency better than
+// 2 A + 6 B stages. Kept selectable because it is the right design if the L2 path ever becomes the limiter.
+//
 // CTA = 320 threads, persistent over 128x256 output tiles:
 //   warp 0      TMA producer (one elected lane), 4-stage ring of {A 128x64, B 256x64} fp16 tiles
 //   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma 128x256x16 per stage
@@ -40,7 +51,10 @@ template <bool PAIR> struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
 };
-constexpr int MAX_BARS = 2 * 6 + 4;
+// barrier slots (8 B each): full_b[8], empty_b[8], full_a[2], empty_a[2], tmem_full[2], tmem_empty[2]. Without halo
+// mode a stage holds {A, B} together and only the *_b barriers are used.
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_BARS = 2 * MAX_STAGES + 4 + 4;
 constexpr int EPI_WARPS = 16;                 // 4 per TMEM lane quarter, 64 accumulator columns each
 constexpr int EPI_COLS = BLOCK_N / (EPI_WARPS / 4);   // 64
 constexpr int CW = 16;                        // columns per tcgen05.ld chunk
@@ -77,7 +91,19 @@ struct TcParams {
   const float* ln_gamma;   // MODE 2 only: LayerNorm over the 256 output columns (N == 256), fused after bias + residual;
   const float* ln_beta;    //   writes the fp32 stream (C32, may alias res32) and its fp16 copy (C16)
   int dbg;                 // bottleneck experiments (TAG_TC_DEBUG): 1 no epilogue stores, 2 no weight loads, 4 no activation loads
+  // halo mode (conv): A chunk loaded once per 64 channels with its time halo, taps = shifted descriptor views
+  int halo;                // 0 off, 1 on, 2 on with the descriptor base-offset field set for unaligned tap shifts (experiment)
+  int a_stage_bytes;       // bytes of one staged A chunk (multiple of 1024); two A stages
+  int a_box_bytes;         // bytes the TMA box delivers (zero-filled rows included)
+  int b_stages;            // weight-tile stages behind the two A stages
+  int tap_rows;            // dil * NW: shared-memory rows between consecutive taps
+  int lw, lt;              // log2(windows per tile), log2(frames per window): tile row r <-> window r & (NW-1), frame r >> lw
 };
+
+// global row of tile row rt (identity unless the tile is (t, window)-ordered)
+__device__ __forceinline__ int64_t tile_row(int64_t tile_base, int rt, int lw, int lt) {
+  return tile_base + (int64_t)(((rt & ((1 << lw) - 1)) << lt) | (rt >> lw));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -169,6 +195,10 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// same with the matrix base-offset field (bits 49-51) = position of the start row inside its 8-row swizzle atom
+__device__ __forceinline__ uint64_t make_smem_desc_off(uint32_t saddr) {
+  return make_smem_desc(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
+}
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -231,10 +261,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
 }
 // coalesced global -> registers of one 32-row x 64-byte unit (rows row0.., byte offset `off` in each row of pitch
 // `pitch` bytes); rows >= M read as zero
-__device__ __forceinline__ void unit_load(const char* base, int64_t pitch, int64_t row0, int64_t M, int64_t off, int lane, uint4 (&r)[4]) {
+struct RowMap { int64_t tile_base; int rt0; int lw, lt; };      // rows rt0.. of the tile starting at global row tile_base
+__device__ __forceinline__ void unit_load(const char* base, int64_t pitch, const RowMap& rm, int64_t M, int64_t off, int lane, uint4 (&r)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int64_t row = row0 + 8 * j + (lane >> 2);
+    const int64_t row = tile_row(rm.tile_base, rm.rt0 + 8 * j + (lane >> 2), rm.lw, rm.lt);
     r[j] = (base != nullptr && row < M) ? __ldg(reinterpret_cast<const uint4*>(base + row * pitch + off + (lane & 3) * 16))
                                         : make_uint4(0u, 0u, 0u, 0u);
   }
@@ -244,10 +275,10 @@ __device__ __forceinline__ void unit_to_smem(uint32_t stg, int lane, const uint4
   for (int j = 0; j < 4; ++j) sts128(stg_addr(stg, 8 * j + (lane >> 2), lane & 3), r[j]);
 }
 // staging tile -> global, coalesced
-__device__ __forceinline__ void unit_store(char* base, int64_t pitch, int64_t row0, int64_t M, int64_t off, int lane, uint32_t stg) {
+__device__ __forceinline__ void unit_store(char* base, int64_t pitch, const RowMap& rm, int64_t M, int64_t off, int lane, uint32_t stg) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int64_t row = row0 + 8 * j + (lane >> 2);
+    const int64_t row = tile_row(rm.tile_base, rm.rt0 + 8 * j + (lane >> 2), rm.lw, rm.lt);
     const uint4 v = lds128(stg_addr(stg, 8 * j + (lane >> 2), lane & 3));
     if (row < M) *reinterpret_cast<uint4*>(base + row * pitch + off + (lane & 3) * 16) = v;
   }
@@ -319,11 +350,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const bool leader = rank == 0;
   constexpr bool GN = MODE == 1;
   constexpr bool LN = MODE == 2;
-  // barrier slots (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base word
+  // barrier slots (8 B each, layout at MAX_BARS); then the TMEM base word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto fulla_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto emptya_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 4 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 6 + a); };
   const uint32_t tmem_slot = bar_base + 8u * MAX_BARS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,7 +369,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * (PAIR ? 2 : 1)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -367,6 +401,44 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (lane == 0) {
       // ================= TMA producer =================
       int stage = 0; uint32_t phase = 0;
+      int sa_i = 0; uint32_t pa = 0;
+      const bool ld_a = !(p.dbg & 4), ld_b = !(p.dbg & 2);
+      if (p.halo) {
+        const int pad = (p.taps / 2) * p.dil;
+        const uint32_t b_ring = smem_base + 2u * (uint32_t)p.a_stage_bytes;
+        for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+          const int64_t m_tile = m_tile_of(tile);
+          const int n_tile = (int)(tile % p.n_tiles);
+          int cw, ct;                                           // window / frame coordinate of the box
+          if (p.mode == 1) { cw = (int)(m_tile * p.wpt); ct = -pad; }
+          else { cw = (int)(m_tile / p.tpw); ct = (int)(m_tile - (int64_t)cw * p.tpw) * BLOCK_M - pad; }
+          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+            mbar_wait(emptya_bar(sa_i), pa ^ 1u);
+            const uint32_t da = smem_base + (uint32_t)(sa_i * p.a_stage_bytes);
+            if constexpr (PAIR) {
+              if (leader) { if (ld_a) mbar_arrive_expect_tx(fulla_bar(sa_i), 2u * (uint32_t)p.a_box_bytes); else mbar_arrive(fulla_bar(sa_i)); }
+              if (ld_a) tma_load_3d_pair(da, &map_a, fulla_bar(sa_i), kc * BLOCK_K, cw, ct);
+            } else {
+              if (ld_a) { mbar_arrive_expect_tx(fulla_bar(sa_i), (uint32_t)p.a_box_bytes); tma_load_3d(da, &map_a, fulla_bar(sa_i), kc * BLOCK_K, cw, ct); }
+              else mbar_arrive(fulla_bar(sa_i));
+            }
+            if (++sa_i == 2) { sa_i = 0; pa ^= 1u; }
+            for (int j = 0; j < p.taps; ++j) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t db = b_ring + (uint32_t)(stage * Cfg<PAIR>::B_BYTES);
+              const int kcoord = (j * p.kb_per_tap + kc) * BLOCK_K;
+              if constexpr (PAIR) {
+                if (leader) { if (ld_b) mbar_arrive_expect_tx(full_bar(stage), 2u * Cfg<PAIR>::B_BYTES); else mbar_arrive(full_bar(stage)); }
+                if (ld_b) tma_load_2d_pair(db, &map_b, full_bar(stage), kcoord, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+              } else {
+                if (ld_b) { mbar_arrive_expect_tx(full_bar(stage), Cfg<PAIR>::B_BYTES); tma_load_2d(db, &map_b, full_bar(stage), kcoord, n_tile * BLOCK_N); }
+                else mbar_arrive(full_bar(stage));
+              }
+              if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      } else
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         const int64_t m_tile = m_tile_of(tile);
         const int n_tile = (int)(tile % p.n_tiles);
@@ -380,7 +452,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const int shift = (p.taps > 1) ? (j - p.taps / 2) * p.dil : 0;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
-          const bool ld_a = !(p.dbg & 4), ld_b = !(p.dbg & 2);
           const uint32_t tx = (ld_a ? A_BYTES : 0) + (ld_b ? Cfg<PAIR>::B_BYTES : 0);
           if constexpr (PAIR) {
             if (leader) { if (tx) mbar_arrive_expect_tx(full_bar(stage), 2 * tx); else mbar_arrive(full_bar(stage)); }   // bytes of both CTAs
@@ -399,6 +470,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     if (lane == 0 && leader) {
       // ================= MMA issuer (leader CTA of a pair) =================
       int stage = 0; uint32_t phase = 0;
+      int sa_i = 0; uint32_t pa = 0;
       int64_t it = 0;
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int acc = (int)(it & 1);
@@ -406,6 +478,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);           // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        if (p.halo) {
+          const uint32_t b_ring = smem_base + 2u * (uint32_t)p.a_stage_bytes;
+          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+            mbar_wait(fulla_bar(sa_i), pa);                     // this 64-channel chunk (with its time halo) has landed
+            tc_fence_after();
+            const uint32_t a_chunk = smem_base + (uint32_t)(sa_i * p.a_stage_bytes);
+            for (int j = 0; j < p.taps; ++j) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint32_t a_tap = a_chunk + (uint32_t)(j * p.tap_rows) * 128u;      // tap j = the same tile, j*dil frames later
+              const uint64_t adesc = p.halo == 2 ? make_smem_desc_off(a_tap) : make_smem_desc(a_tap);
+              const uint64_t bdesc = make_smem_desc(b_ring + (uint32_t)(stage * Cfg<PAIR>::B_BYTES));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                if constexpr (PAIR) umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kc | j | k) != 0 ? 1u : 0u);
+                else umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), Cfg<PAIR>::IDESC, (kc | j | k) != 0 ? 1u : 0u);
+              }
+              if constexpr (PAIR) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+              if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
+            }
+            if constexpr (PAIR) umma_commit_pair(emptya_bar(sa_i)); else umma_commit(emptya_bar(sa_i));
+            if (++sa_i == 2) { sa_i = 0; pa ^= 1u; }
+          }
+        } else
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);                  // TMA bytes have landed
           tc_fence_after();
@@ -439,7 +535,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const int n_tile = (int)(tile % p.n_tiles);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int64_t row0 = m_tile * BLOCK_M + q * 32;          // first row of this warp
+      const RowMap rm{m_tile * BLOCK_M, q * 32, p.lw, p.lt};   // this warp's 32 tile rows -> global rows
+      const bool my_row_valid = tile_row(rm.tile_base, rm.rt0 + lane, rm.lw, rm.lt) < p.M;
       const int n_base = n_tile * BLOCK_N + part * EPI_COLS;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + part * EPI_COLS);
       if constexpr (GN) {
@@ -447,14 +544,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint32_t stash[EPI_COLS / 2];
         float s1 = 0.f, s2 = 0.f;
         uint4 rres[4];
-        unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)n_base * 2, lane, rres);
+        unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll
         for (int u = 0; u < 2; ++u) {                           // units of 32 fp16 columns
           unit_to_smem(stg, lane, rres);
           __syncwarp();
-          if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
+          if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c = u * 2 + cc;
@@ -463,7 +560,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tmem_ld16_wait(raw);
             float v[CW];
             epi_values<16>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
-            if (row0 + lane >= p.M) {
+            if (!my_row_valid) {
 #pragma unroll
               for (int i = 0; i < CW; ++i) v[i] = 0.f;
             }
@@ -482,23 +579,39 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
         // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 4 column parts
-        const int width = p.T < 32 ? p.T : 32;
-        for (int o = width >> 1; o > 0; o >>= 1) {
-          s1 += __shfl_xor_sync(FULL_MASK, s1, o);
-          s2 += __shfl_xor_sync(FULL_MASK, s2, o);
-        }
-        const int G = p.T > 32 ? p.T / 32 : 1;
         const uint32_t red = bar_base + 256u + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + q / G), "r"(4 * G * 32) : "memory");
         float S1 = 0.f, S2 = 0.f;
-        for (int qq = 0; qq < G; ++qq) {
+        if (p.halo) {
+          // (t, window)-ordered tile: lane l of EVERY epilogue warp holds rows of window l & (NW-1)
+          for (int o = 16; o >= (1 << p.lw); o >>= 1) {
+            s1 += __shfl_xor_sync(FULL_MASK, s1, o);
+            s2 += __shfl_xor_sync(FULL_MASK, s2, o);
+          }
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(1), "r"(EPI_WARPS * 32) : "memory");
 #pragma unroll
-          for (int pp = 0; pp < EPI_WARPS / 4; ++pp) {
-            const int e = pp * 4 + ((((q / G) * G + qq) - 2) & 3);
+          for (int e = 0; e < EPI_WARPS; ++e) {
             float a, b;
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)((e * 32 + lane) * 8)) : "memory");
             S1 += a; S2 += b;
+          }
+        } else {
+          const int width = p.T < 32 ? p.T : 32;
+          for (int o = width >> 1; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(FULL_MASK, s1, o);
+            s2 += __shfl_xor_sync(FULL_MASK, s2, o);
+          }
+          const int G = p.T > 32 ? p.T / 32 : 1;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + q / G), "r"(4 * G * 32) : "memory");
+          for (int qq = 0; qq < G; ++qq) {
+#pragma unroll
+            for (int pp = 0; pp < EPI_WARPS / 4; ++pp) {
+              const int e = pp * 4 + ((((q / G) * G + qq) - 2) & 3);
+              float a, b;
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)((e * 32 + lane) * 8)) : "memory");
+              S1 += a; S2 += b;
+            }
           }
         }
         const float inv_n = 1.0f / ((float)p.T * (float)BLOCK_N);
@@ -530,21 +643,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             sts128(stg_addr(stg, lane, i), o);
           }
           __syncwarp();
-          unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(nl + u * 32) * 2, lane, stg);
+          unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(nl + u * 32) * 2, lane, stg);
           __syncwarp();
         }
       } else if constexpr (LN) {
         // ---- pass 1: v = acc + bias + x (fp32 residual, staged coalesced), row sums, v parked back into TMEM
         float s1 = 0.f, s2 = 0.f;
         uint4 rres[4];
-        unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)n_base * 4, lane, rres);
+        unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, rm, p.M, (int64_t)n_base * 4, lane, rres);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           unit_to_smem(stg, lane, rres);
           __syncwarp();
-          if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + (u + 1) * CW) * 4, lane, rres);
+          if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, rm, p.M, (int64_t)(n_base + (u + 1) * CW) * 4, lane, rres);
           uint32_t raw[CW];
           tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
           tmem_ld16_wait(raw);
@@ -605,13 +718,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             h16[(u & 1) * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&t);
           }
           __syncwarp();
-          unit_store(reinterpret_cast<char*>(p.C32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + u * CW) * 4, lane, stg);
+          unit_store(reinterpret_cast<char*>(p.C32), (int64_t)p.N * 4, rm, p.M, (int64_t)(n_base + u * CW) * 4, lane, stg);
           __syncwarp();
           if (u & 1) {                                          // two units done: 32 fp16 columns = one 64-byte unit
 #pragma unroll
             for (int i = 0; i < 4; ++i) sts128(stg_addr(stg, lane, i), make_uint4(h16[i * 4], h16[i * 4 + 1], h16[i * 4 + 2], h16[i * 4 + 3]));
             __syncwarp();
-            unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(n_base + (u - 1) * CW) * 2, lane, stg);
+            unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(n_base + (u - 1) * CW) * 2, lane, stg);
             __syncwarp();
           }
         }
@@ -619,7 +732,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         // ---- fp16 output (optional fp16 residual): 2 units of 32 columns
         const bool has_res = p.res16 != nullptr;
         uint4 rres[4];
-        if (has_res) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)n_base * 2, lane, rres);
+        if (has_res) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll
@@ -627,7 +740,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (has_res) {
             unit_to_smem(stg, lane, rres);
             __syncwarp();
-            if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, row0, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
+            if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
           }
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -653,14 +766,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
           }
           __syncwarp();
-          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, row0, p.M, (int64_t)(n_base + u * 32) * 2, lane, stg);
+          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(n_base + u * 32) * 2, lane, stg);
           __syncwarp();
         }
       } else {
         // ---- fp32 output (optional fp32 residual, ld = N): 4 units of 16 columns
         const bool has_res = p.res32 != nullptr;
         uint4 rres[4];
-        if (has_res) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)n_base * 4, lane, rres);
+        if (has_res) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, rm, p.M, (int64_t)n_base * 4, lane, rres);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
 #pragma unroll
@@ -668,7 +781,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           if (has_res) {
             unit_to_smem(stg, lane, rres);
             __syncwarp();
-            if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + (u + 1) * CW) * 4, lane, rres);
+            if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, rm, p.M, (int64_t)(n_base + (u + 1) * CW) * 4, lane, rres);
           }
           uint32_t raw[CW];
           tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
@@ -686,7 +799,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
           }
           __syncwarp();
-          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C32), (int64_t)p.N * 4, row0, p.M, (int64_t)(n_base + u * CW) * 4, lane, stg);
+          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C32), (int64_t)p.N * 4, rm, p.M, (int64_t)(n_base + u * CW) * 4, lane, stg);
           __syncwarp();
         }
       }
@@ -714,6 +827,9 @@ struct TcContext {
   int num_sms = 148;
   bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
   int dbg = 0;            // TAG_TC_DEBUG bottleneck experiments (results are wrong when set)
+  int halo = 0;           // TAG_TC_HALO: 0 five shifted loads per chunk (default), 1 halo tiles when the tap shift is 8-row
+                          // aligned, 2 halo tiles for every dilation (unaligned descriptor start address: correct on B200),
+                          // 3 = 2 with the descriptor base-offset field set (WRONG results on B200; kept as a probe)
 };
 
 TcContext* tc_context_create(int device, char* err, int errlen) {
@@ -739,6 +855,8 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   if (env != nullptr) c->pair = env[0] != '0';
   env = getenv("TAG_TC_DEBUG");
   if (env != nullptr) c->dbg = atoi(env);
+  env = getenv("TAG_TC_HALO");
+  if (env != nullptr) c->halo = atoi(env);
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
     delete c;
@@ -794,7 +912,40 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
 
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t box[3], estr[3] = {1, 1, 1};
-  if (g.taps > 1) {
+  const bool pair = ctx->pair && p.m_tiles >= 2;
+  const int b_bytes = (pair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
+  if (g.taps > 1 && ctx->halo != 0 && (g.taps & 1)) {
+    // halo tiles: (t, window)-ordered rows, one load per 64-channel chunk (see the header comment)
+    if (g.T >= 1 && g.M % g.T == 0 && ((g.T <= BLOCK_M && BLOCK_M % g.T == 0) || g.T % BLOCK_M == 0)) {
+      const int tp = g.T <= BLOCK_M ? g.T : BLOCK_M;              // frames of a tile
+      const int nw = BLOCK_M / tp;                                // windows of a tile
+      const int pad = (g.taps / 2) * g.dil;
+      const int rows = nw * (tp + 2 * pad);
+      const int a_stage = (rows * 128 + 1023) & ~1023;
+      const int b_stages = (RING_BYTES - 2 * a_stage) / b_bytes;
+      const bool aligned = (g.dil * nw) % 8 == 0;
+      if (nw <= 32 && tp + 2 * pad <= 256 && g.dil >= 1 && b_stages >= 2 && (aligned || ctx->halo >= 2)) {
+        int lw = 0, lt = 0;
+        while ((1 << lw) < nw) ++lw;
+        while ((1 << lt) < tp) ++lt;
+        p.halo = (!aligned && ctx->halo == 3) ? 2 : 1;
+        p.a_stage_bytes = a_stage; p.a_box_bytes = rows * 128;
+        p.b_stages = b_stages < MAX_STAGES ? b_stages : MAX_STAGES;
+        p.tap_rows = g.dil * nw;
+        p.lw = nw > 1 ? lw : 0; p.lt = lt;
+      }
+    }
+  }
+  if (p.halo) {
+    const int64_t W = g.M / g.T;
+    const int tp = g.T <= BLOCK_M ? g.T : BLOCK_M;
+    if (g.T <= BLOCK_M) { p.mode = 1; p.wpt = BLOCK_M / g.T; p.tpw = 1; }
+    else { p.mode = 2; p.wpt = 1; p.tpw = g.T / BLOCK_M; }
+    const int pad = (g.taps / 2) * g.dil;
+    box[0] = BLOCK_K; box[1] = (cuuint32_t)p.wpt; box[2] = (cuuint32_t)(tp + 2 * pad);
+    gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)W; gdim[2] = (cuuint64_t)g.T;
+    gstr[0] = (cuuint64_t)g.T * g.lda * 2; gstr[1] = (cuuint64_t)g.lda * 2;
+  } else if (g.taps > 1) {
     if (g.T < 1 || g.M % g.T) return bad("conv rows must be whole windows");
     const int64_t W = g.M / g.T;
     if (g.T <= BLOCK_M) {
@@ -822,7 +973,6 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   const int64_t ktot = (int64_t)g.taps * g.K;
   cuuint64_t bdim[2] = {(cuuint64_t)ktot, (cuuint64_t)g.N};
   cuuint64_t bstr[1] = {(cuuint64_t)ktot * 2};
-  const bool pair = ctx->pair && p.m_tiles >= 2;
   cuuint32_t bbox[2] = {BLOCK_K, (cuuint32_t)(pair ? BLOCK_N / 2 : BLOCK_N)};
   cuuint32_t bes[2] = {1, 1};
   r = ctx->encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(g.W), bdim, bstr, bbox, bes,
