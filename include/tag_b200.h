@@ -163,6 +163,13 @@ int tag_get_profile(tag_handle* h, double* out12);
 int tag_debug_gemm_f32(tag_handle* h, const float* A, int32_t lda, const float* W, int32_t ldw, int64_t M, int32_t N,
                        int32_t K, int32_t taps, int32_t dil, int32_t T, const float* bias, const float* res, float* C,
                        int32_t act, void* stream);
+/* K1 in its tensor-core-path form: the padded fp16 operand [n_windows*T, D16] the encoder's stem GEMMs read (every
+ * modality block padded to a multiple of 64 columns: raw blocks in modality order, then diff blocks; pad columns zero).
+ * This is what tag_encode_windows builds internally; exposed so the tests can compare it with tag_feature_fuse.
+ * Returns D16 through *d16_out (call with feats16_out == NULL to query it). */
+int tag_debug_feature_fuse16(tag_handle* h, const tag_videos* vids, const float* mean, const float* stdv,
+                             const int32_t* win_video, const int32_t* win_start, int64_t n_windows, int32_t T,
+                             void* feats16_out, int32_t* d16_out, int32_t* flags_out, void* stream);
 int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, int64_t M, int32_t N, int32_t K,
                       int32_t taps, int32_t dil, int32_t T, const float* bias, const void* res16, const float* res32,
                       void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta,

@@ -79,6 +79,64 @@ def test_feature_fuse_slice_or_pad_edges():
         assert max_abs(feats[i].cpu(), ref) < 2e-6, (v, s)
 
 
+@pytest.mark.parametrize("tag,with_stats", [("m5_t32", True), ("m5_t32", False), ("m7_t256", True)])
+def test_feature_fuse_fp16_operand_matches_fp32_features(tag, with_stats):
+    """The tensor-core path's K1 (shared-memory staged kernel, padded fp16 rows) against the fp32 K1 output on the same
+    windows — regular windows plus every slice-or-pad edge (negative / out-of-range start, ragged tail, short video):
+    same values up to fp16 rounding, pad columns exactly zero."""
+    g = golden_case(tag)
+    dv, fuser = _dv_and_fuser(g, g.gen)
+    T = g.clip_len
+    lens = [g.gen.length(v) for v in range(g.gen.n_videos)]
+    vs = int(np.argmin(lens))                                   # the shortest video: ragged tails / short-video padding
+    wins = list(g.gen_windows()) + [(0, -3), (0, lens[0]), (0, lens[0] - 4), (vs, 0), (vs, 3), (vs, lens[vs] // 2)]
+    wv = torch.tensor([c[0] for c in wins], dtype=torch.int32, device=DEV)
+    ws = torch.tensor([c[1] for c in wins], dtype=torch.int32, device=DEV)
+    mean = std = None
+    if with_stats:
+        mean, std = tb.features.stats_vectors(g.stats(), g.mods, DEV)
+    feats, flags = fuser.fuse(dv, wv, ws, T, mean, std)
+    lib = _lib.load()
+    d16 = C.c_int32(0)
+    _lib.check(fuser.handle, lib.tag_debug_feature_fuse16(fuser.handle, C.byref(dv.c), None, None, None, None, 0, T, None,
+                                                          C.byref(d16), None, None), "d16")
+    D16 = d16.value
+    N = len(wins)
+    f16 = torch.full((N * T, D16), float("nan"), device=DEV, dtype=torch.float16)
+    flags16 = torch.zeros(1, device=DEV, dtype=torch.int32)
+    _lib.check(fuser.handle, lib.tag_debug_feature_fuse16(fuser.handle, C.byref(dv.c), _lib.ptr(mean), _lib.ptr(std), wv.data_ptr(),
+                                                          ws.data_ptr(), N, T, f16.data_ptr(), C.byref(d16), flags16.data_ptr(),
+                                                          torch.cuda.current_stream().cuda_stream), "tag_debug_feature_fuse16")
+    torch.cuda.synchronize()
+    assert int(flags16.item()) == int(flags.item())
+    # expected operand: every block padded to 64 columns, raw blocks then diff blocks
+    exp = torch.zeros(N * T, D16, device=DEV, dtype=torch.float32)
+    f2 = feats.reshape(N * T, -1)
+    src = dst = 0
+    for dims in (g.dims_raw, g.dims_diff):
+        for m in g.mods:
+            d = int(dims[m])
+            exp[:, dst:dst + d] = f2[:, src:src + d]
+            src += d
+            dst += (d + 63) // 64 * 64
+    assert dst == D16 and src == f2.shape[1]
+    got = f16.float()
+    assert torch.isfinite(got).all()
+    pad = torch.ones(D16, dtype=torch.bool, device=DEV)
+    dst = 0
+    for dims in (g.dims_raw, g.dims_diff):
+        for m in g.mods:
+            d = int(dims[m])
+            pad[dst:dst + d] = False
+            dst += (d + 63) // 64 * 64
+    assert float(got[:, pad].abs().max()) == 0.0
+    # fp16 rounding of the same fp32 value: half an ulp (2^-11 relative) plus the two kernels' own fp32 differences
+    err = (got - exp).abs()
+    tol = exp.abs() * 2.0 ** -10 + 3e-4
+    assert bool((err <= tol).all()), f"max err {float(err.max()):.3e} at {int(err.argmax())}"
+    assert float(err.median()) < 2e-4
+
+
 def test_feature_fuse_reflection_flag():
     """i.i.d. random keypoint frames land in the det(H) < 0 regime about half of the time; the kernel must
     count them (known divergence) and agree with the oracle's count."""

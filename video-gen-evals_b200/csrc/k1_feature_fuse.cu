@@ -256,98 +256,115 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
 
 // ------------------------------------------------------------------------------------------------------------------
 // Shared-memory staged variant for the tensor-core path (fp16 padded output only).
-// One CTA = one window x kS = 8 consecutive frames, one warp per frame:
-//   load    the kS+1 source rows of every modality land in shared memory first — the wide cosine rows by
-//           cp.async.bulk (one 16-byte-aligned row per copy, completion on an mbarrier), the small modalities by
-//           coalesced loads issued up front by all 256 threads — so a CTA has ~49 KB of reads in flight at once
-//           instead of a chain of dependent per-modality round trips;
-//   compute each warp builds its frame's [raw || diff] row (z-scored, fp16, pad columns zero) in shared memory;
+// One CTA = one window x kS = 4 consecutive frames ("slots" 0..kS hold source frames t0-1 .. t0+kS-1):
+//   load    every modality's slots land in shared memory first. Modalities whose rows are 16-byte friendly (vit, clip,
+//           dino, kp2d) take one cp.async.bulk per slot, completing on an mbarrier; the others (9 / 207 / 10 floats
+//           per row) are copied as ONE flat coalesced range when the slots are consecutive source frames (always,
+//           except in nearest-repeat padded windows), compactly at a pitch of `dim` floats;
+//   phase A warps 0..3 align the keypoints of frame `warp` (shuffle reductions); warps 4..7 take the cosine row norms,
+//           the rotation-log joints (one (frame, joint) pair per lane, all rotation modalities in one item list), the
+//           z-scored raw columns and plain differences of the small modalities (32-column chunks from a host-built
+//           chunk list) — all independent, so no warp waits for another;
+//   phase B all 256 threads stream the cosine modalities: 4 columns per thread, the four z-score table float4s loaded
+//           once, the previous frame's normalised values carried in registers across the kS frames;
 //   store   the kS output rows of a block are contiguous in feats16: ONE cp.async.bulk shared->global per CTA.
-// kS = 4 frames per CTA: 5 input rows (27 KB) + 4 output rows (23 KB) -> 4 CTAs (32 warps) per SM, so one CTA's load
-// phase overlaps the others' compute/store phases (kS = 8 left only 2 CTAs per SM and measured slower).
+// ~51 KB of shared memory -> 4 CTAs (32 warps) per SM, so one CTA's load phase overlaps the others' compute / store.
+// The first staged version spent 3,445 warp instructions per frame (ncu: issue slots 65 % busy, DRAM 15 %): 64-bit
+// index divisions, eight predicated load/store slots per small row whatever its width, per-element table loads and
+// 8-warp loops over 9-column modalities. The host-built plan below removes the per-element bookkeeping.
 constexpr int kStagedFrames = 4;
+constexpr int kMaxRawChunks = 48, kMaxPlainChunks = 16, kMaxRotItems = 64;
+
+struct StagedPlan {
+  int bpw;                                   // blocks (of kS frames) per window
+  int wide_pitch;                            // floats between slots of the bulk-copied modalities
+  int out_off, inv_off, bar_off;             // byte offsets in dynamic shared memory (staging area at 0)
+  int base_off[TAG_MAX_MODALITIES];          // float offset of slot 0 of modality m
+  int pitch[TAG_MAX_MODALITIES];             // floats between its slots (wide_pitch, or dim when compact)
+  unsigned char bulk[TAG_MAX_MODALITIES];    // 1: one cp.async.bulk per slot
+  int n_raw, n_plain, n_rot, n_proc, n_cos;
+  unsigned char raw_mod[kMaxRawChunks];   short raw_col[kMaxRawChunks];      // z-scored raw copies, 32 columns per chunk
+  unsigned char plain_mod[kMaxPlainChunks]; short plain_col[kMaxPlainChunks];
+  unsigned char rot_mod[kMaxRotItems];    unsigned char rot_joint[kMaxRotItems];
+  unsigned char proc_mod[TAG_MAX_MODALITIES];
+  unsigned char cos_mod[TAG_MAX_MODALITIES];
+};
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int kS>
-__global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, int in_floats_per_row, int smem_in_bytes, int dbg) {
+__global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, const StagedPlan pl, int dbg) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
-  float* s_in = reinterpret_cast<float*>(sm_raw);                                   // [kS+1][in_floats_per_row]
-  __half* s_out = reinterpret_cast<__half*>(sm_raw + smem_in_bytes);               // [kS][D16]
-  float* s_inv = reinterpret_cast<float*>(sm_raw + smem_in_bytes + kS * p.D16 * 2); // [M][kS+1]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_inv + TAG_MAX_MODALITIES * (kS + 1) + 2);
+  float* s_in = reinterpret_cast<float*>(sm_raw);
+  __half* s_out = reinterpret_cast<__half*>(sm_raw + pl.out_off);                  // [kS][D16]
+  float* s_inv = reinterpret_cast<float*>(sm_raw + pl.inv_off);                    // [n_cos][kS+1]
+  const uint32_t bar = smem_addr(sm_raw + pl.bar_off);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int blocks_per_win = (p.T + kS - 1) / kS;
-  const int64_t w = blockIdx.x / blocks_per_win;
-  const int t0 = (int)(blockIdx.x - w * blocks_per_win) * kS;
+  const unsigned w = blockIdx.x / (unsigned)pl.bpw;
+  const int t0 = (int)(blockIdx.x - w * (unsigned)pl.bpw) * kS;
   const int nf = min(kS, p.T - t0);
   const int vid = p.win_video[w];
   const int start = p.win_start[w];
   const int64_t f0 = p.frame_offset[vid];
   const int L = (int)(p.frame_offset[vid + 1] - f0);
-  auto row_of = [&](int t) -> int64_t { return f0 + src_frame(start, t < 0 ? 0 : t, L); };
-  const uint32_t bar = smem_addr(s_bar);
+  const int k0 = t0 == 0 ? 1 : 0;                    // slot 0 (= the frame before the window) duplicates slot 1
+  // slots k0..nf are consecutive source frames unless the window is padded (utils.py:371-381)
+  const bool consec = start >= 0 && start + t0 + nf - 1 <= L - 1;
+  auto row_of_slot = [&](int k) -> int64_t { const int t = t0 - 1 + k; return f0 + src_frame(start, t < 0 ? 0 : t, L); };
 
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero the output tile (pad columns stay zero)
-  for (int i = tid; i < kS * p.D16 / 8; i += 256) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0u, 0u, 0u, 0u);
+  {  // zero the output tile (pad columns stay zero)
+    uint4* z = reinterpret_cast<uint4*>(s_out);
+    const int n16 = kS * p.D16 / 8;
+#pragma unroll 2
+    for (int i = tid; i < n16; i += 256) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
 
   // ---- load phase
-  int col = 0;                                   // float offset of modality m inside a staged row
-  uint32_t tx = 0;
-#pragma unroll 1
-  for (int m = 0; m < p.M; ++m) {
-    const int dim = p.raw_dim[m];
-    if (p.kind[m] == TAG_KIND_COSINE) tx += (uint32_t)((nf + 1) * dim * 4);
-    col += (dim + 3) & ~3;
-  }
-  if (dbg & 4) tx = 0;                           // experiment: no loads
-  if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
-  __syncthreads();
-  col = 0;
-#pragma unroll 1
-  for (int m = 0; m < p.M; ++m) {
-    const int dim = p.raw_dim[m];
-    const float* src = p.src[m];
-    if (dbg & 4) { col += (dim + 3) & ~3; continue; }
-    if (p.kind[m] == TAG_KIND_COSINE) {
-      if (tid <= nf) {                           // one bulk copy per row (rows may repeat when the window is padded)
-        const float* g = src + row_of(t0 + tid - 1) * dim;
-        const uint32_t d = smem_addr(s_in + tid * in_floats_per_row + col);
+  if (warp == 0) {
+    uint32_t tx = 0;
+    if (!(dbg & 4))
+      for (int m = 0; m < p.M; ++m) if (pl.bulk[m]) tx += (uint32_t)((nf + 1) * p.raw_dim[m] * 4);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+    __syncwarp();
+    if (lane <= nf && !(dbg & 4)) {                   // lane k issues the bulk copies of slot k
+      const int64_t r = row_of_slot(lane);
+      for (int m = 0; m < p.M; ++m) {
+        if (!pl.bulk[m]) continue;
+        const int dim = p.raw_dim[m];
+        const float* g = p.src[m] + r * dim;
+        const uint32_t d = smem_addr(s_in + pl.base_off[m] + lane * pl.wide_pitch);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(d), "l"(g), "r"((uint32_t)(dim * 4)), "r"(bar) : "memory");
       }
-    } else {
-      // warp r stages rows r and r+8 (only warp 0 has a second row). Explicit register batches: all loads of both rows
-      // are issued before the first store — the compiler's own unrolling left a one-load-one-store remainder loop
-      // (dim < 256) that paid a DRAM round trip per element, 28 % of the kernel's stall samples.
-      const int r1 = warp, r2 = warp + 8;
-      const float* g1 = src + row_of(t0 + r1 - 1) * dim;
-      const float* g2 = src + row_of(t0 + (r2 <= nf ? r2 : r1) - 1) * dim;
-      for (int i0 = 0; i0 < dim; i0 += 256) {
-        float v[8], u[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int i = i0 + k * 32 + lane;
-          v[k] = (r1 <= nf && i < dim) ? __ldg(g1 + i) : 0.f;
-          u[k] = (r2 <= nf && i < dim) ? __ldg(g2 + i) : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int i = i0 + k * 32 + lane;
-          if (r1 <= nf && i < dim) s_in[r1 * in_floats_per_row + col + i] = v[k];
-          if (r2 <= nf && i < dim) s_in[r2 * in_floats_per_row + col + i] = u[k];
+    }
+  }
+  if (!(dbg & 4)) {
+#pragma unroll 1
+    for (int m = 0; m < p.M; ++m) {
+      if (pl.bulk[m]) continue;
+      const int dim = p.raw_dim[m];
+      float* dst = s_in + pl.base_off[m];
+      if (consec) {                                   // one flat coalesced range
+        const float* g = p.src[m] + (f0 + start + t0 - 1 + k0) * dim;
+        const int n = (nf + 1 - k0) * dim;
+        dst += k0 * dim;
+#pragma unroll 4
+        for (int i = tid; i < n; i += 256) dst[i] = __ldg(g + i);
+      } else {
+        for (int k = k0; k <= nf; ++k) {
+          const float* g = p.src[m] + row_of_slot(k) * dim;
+          for (int i = tid; i < dim; i += 256) dst[k * dim + i] = __ldg(g + i);
         }
       }
     }
-    col += (dim + 3) & ~3;
   }
-  {  // wait for the bulk copies (bounded: a protocol bug must not hang the GPU)
+  if (warp == 0) {  // one warp waits for the bulk copies (bounded: a protocol bug must not hang the GPU); the others park at the barrier
     uint32_t ok = 0;
     const long long c0 = clock64();
     while (!ok) {
@@ -358,157 +375,190 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   }
   __syncthreads();
 
-  // ---- row norms of the cosine modalities: one row per warp
-  col = 0;
-#pragma unroll 1
-  for (int m = 0; m < ((dbg & 1) ? 0 : p.M); ++m) {
-    const int dim = p.raw_dim[m];
-    if (p.kind[m] == TAG_KIND_COSINE) {
-      for (int r = warp; r <= nf; r += 8) {                               // one row per warp (two for warp 0 when kS = 8)
-        {
-          const float* x = s_in + r * in_floats_per_row + col;
-          float ss = 0.f;
-          for (int i = 2 * lane; i < dim; i += 64) {
-            const float2 a = *reinterpret_cast<const float2*>(x + i);
-            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss);
-          }
-          ss = warp_sum(ss);
-          if (lane == 0) s_inv[m * (kS + 1) + r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-        }
-      }
-    }
-    col += (dim + 3) & ~3;
-  }
-  __syncthreads();
-
-  // ---- compute phase, item-parallel over the whole CTA (no warp-serial chains): a thread owns a column (pair) for
-  // all nf frames, so its two z-score table entries are loaded once and stay in registers; rotation joints and plain
-  // differences are spread as (frame, item) pairs; only the keypoint alignment is a warp-per-frame reduction.
   const Norm nz{p.mean, p.stdv};
-  col = 0;
-#pragma unroll 1
-  for (int m = 0; m < ((dbg & 1) ? 0 : p.M); ++m) {
-    const int dim = p.raw_dim[m];
-    const float* xin = s_in + col;                       // row r of this modality: xin + r * in_floats_per_row
-    const int ro = p.raw_off[m], dofs = p.diff_off[m];
-    const int ro16 = p.raw_off16[m], do16 = p.diff_off16[m];
-    const int kind = p.kind[m];
-    const bool has_diff = p.diff_dim[m] > 0;
-    col += (dim + 3) & ~3;
-
-    if (kind == TAG_KIND_COSINE) {
-      const float* invm = s_inv + m * (kS + 1);
-      for (int i = 2 * tid; i < dim; i += 512) {
-        float2 sr = make_float2(1.f, 1.f), hr = make_float2(0.f, 0.f), sd = sr, hd = hr;
-        if (nz.scale != nullptr) {
-          sr = *reinterpret_cast<const float2*>(nz.scale + ro + i);    // ro, dofs even on this path (checked on the host)
-          hr = *reinterpret_cast<const float2*>(nz.shift + ro + i);
-          if (has_diff) {
-            sd = *reinterpret_cast<const float2*>(nz.scale + dofs + i);
-            hd = *reinterpret_cast<const float2*>(nz.shift + dofs + i);
-          }
-        }
-        float2 prev = *reinterpret_cast<const float2*>(xin + i);
-        prev.x *= invm[0]; prev.y *= invm[0];
+  if (!(dbg & 1)) {
+    // ================= phase A: independent per-warp jobs =================
+    const bool has_proc = pl.n_proc > 0;
+    if (has_proc && warp < 4) {
+      // ---- keypoint Procrustes delta: warp f aligns frame t0+f-1 -> t0+f (utils.py:177-217)
+      const int f = warp;
+      if (f < nf) {
+        for (int q = 0; q < pl.n_proc; ++q) {
+          const int m = pl.proc_mod[q];
+          const int dim = p.raw_dim[m];
+          const float* xc = s_in + pl.base_off[m] + (f + 1) * pl.pitch[m];
+          const float* xp = s_in + pl.base_off[m] + ((f == 0 && k0) ? 1 : f) * pl.pitch[m];
+          __half* o16 = s_out + f * p.D16 + p.diff_off16[m];
+          const int dofs = p.diff_off[m];
+          const int K = dim / 2;
+          const int k1 = lane + 32;
+          const bool a0 = lane < K, a1 = k1 < K;
+          const float invK = 1.0f / (float)K;
+          // centre + Frobenius-normalise one frame's points (utils.py:192-196)
+          auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
+            const float2 u0 = a0 ? *reinterpret_cast<const float2*>(x + 2 * lane) : make_float2(0.f, 0.f);
+            const float2 u1 = a1 ? *reinterpret_cast<const float2*>(x + 2 * k1) : make_float2(0.f, 0.f);
+            float sx = u0.x + u1.x, sy = u0.y + u1.y;
 #pragma unroll
-        for (int f = 0; f < kS; ++f) {
-          if (f < nf) {
-            const float2 a = *reinterpret_cast<const float2*>(xin + (f + 1) * in_floats_per_row + i);
-            __half* o16 = s_out + f * p.D16;
-            *reinterpret_cast<__half2*>(o16 + ro16 + i) = __floats2half2_rn(fmaf(a.x, sr.x, hr.x), fmaf(a.y, sr.y, hr.y));
-            if (has_diff) {
-              const float2 cur = make_float2(a.x * invm[f + 1], a.y * invm[f + 1]);
-              *reinterpret_cast<__half2*>(o16 + do16 + i) =
-                  __floats2half2_rn(fmaf(cur.x - prev.x, sd.x, hd.x), fmaf(cur.y - prev.y, sd.y, hd.y));
-              prev = cur;
+            for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(FULL_MASK, sx, o); sy += __shfl_xor_sync(FULL_MASK, sy, o); }
+            const float mx = sx * invK, my = sy * invK;
+            x0 = a0 ? u0.x - mx : 0.f; y0 = a0 ? u0.y - my : 0.f;
+            x1 = a1 ? u1.x - mx : 0.f; y1 = a1 ? u1.y - my : 0.f;
+            const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
+            x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
+          };
+          float x0, y0, x1, y1, px0, py0, px1, py1;
+          load_norm(xc, x0, y0, x1, y1);
+          load_norm(xp, px0, py0, px1, py1);
+          float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
+          if (t0 + f > 0) {
+            // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
+            float h00 = px0 * x0 + px1 * x1, h01 = px0 * y0 + px1 * y1, h10 = py0 * x0 + py1 * x1, h11 = py0 * y0 + py1 * y1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              h00 += __shfl_xor_sync(FULL_MASK, h00, o); h01 += __shfl_xor_sync(FULL_MASK, h01, o);
+              h10 += __shfl_xor_sync(FULL_MASK, h10, o); h11 += __shfl_xor_sync(FULL_MASK, h11, o);
             }
+            if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+            // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
+            const float ry = h10 - h01, rx = h00 + h11;
+            const float rr = ry * ry + rx * rx;
+            const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
+            const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
+            d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
+            d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
           }
+          if (a0) *reinterpret_cast<__half2*>(o16 + 2 * lane) = __floats2half2_rn(nz(d00, dofs + 2 * lane), nz(d01, dofs + 2 * lane + 1));
+          if (a1) *reinterpret_cast<__half2*>(o16 + 2 * k1) = __floats2half2_rn(nz(d10, dofs + 2 * k1), nz(d11, dofs + 2 * k1 + 1));
         }
       }
-      continue;
-    }
-    // raw columns of the small modalities: one column per thread, all frames
-    for (int i = tid; i < dim; i += 256) {
-      const float sc = nz.scale ? __ldg(nz.scale + ro + i) : 1.f, sh = nz.scale ? __ldg(nz.shift + ro + i) : 0.f;
-#pragma unroll
-      for (int f = 0; f < kS; ++f)
-        if (f < nf) s_out[f * p.D16 + ro16 + i] = __float2half_rn(fmaf(xin[(f + 1) * in_floats_per_row + i], sc, sh));
-    }
-    if (!has_diff) continue;
-    if (kind == TAG_KIND_ROTMAT) {
-      const int J = dim / 9;
-      for (int jn = lane; warp < nf && jn < J; jn += 32) {     // warp = frame, lane = joint
-        const int f = warp;
-        const float* xc = xin + (f + 1) * in_floats_per_row + jn * 9;
-        const float* xp = xin + f * in_floats_per_row + jn * 9;
+    } else {
+      const int aw = has_proc ? warp - 4 : warp;      // auxiliary warp index
+      const int naw = has_proc ? 4 : 8;
+      // ---- cosine row norms: one (modality, slot) per job
+      for (int j = aw; j < pl.n_cos * (nf + 1); j += naw) {
+        const int q = j / (nf + 1), k = j - q * (nf + 1);
+        const int m = pl.cos_mod[q];
+        const int dim = p.raw_dim[m];
+        const float4* x = reinterpret_cast<const float4*>(s_in + pl.base_off[m] + k * pl.pitch[m]);
+        float ss = 0.f;
+        for (int i = lane; i < dim / 4; i += 32) {
+          const float4 a = x[i];
+          ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss); ss = fmaf(a.z, a.z, ss); ss = fmaf(a.w, a.w, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) s_inv[q * (kS + 1) + k] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      }
+      // ---- rotation log-maps: one (frame, joint) pair per lane (utils.py:165-174, :130-140)
+      for (int e = aw * 32 + lane; e < nf * pl.n_rot; e += naw * 32) {
+        const int f = e / pl.n_rot, it = e - f * pl.n_rot;
+        const int m = pl.rot_mod[it], jn = pl.rot_joint[it];
+        const float* xc = s_in + pl.base_off[m] + (f + 1) * pl.pitch[m] + jn * 9;
+        const float* xp = s_in + pl.base_off[m] + ((f == 0 && k0) ? 1 : f) * pl.pitch[m] + jn * 9;
         float R[9], Q[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) { R[k] = xc[k]; Q[k] = xp[k]; }
-        // Rrel = Q^T R  (utils.py:172), entries [i][j] = sum_k Q[k][i] R[k][j]
-        float E[9];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            E[i * 3 + j] = Q[0 * 3 + i] * R[0 * 3 + j] + Q[1 * 3 + i] * R[1 * 3 + j] + Q[2 * 3 + i] * R[2 * 3 + j];
-        float tr = E[0] + E[4] + E[8];
+        // Rrel = Q^T R  (utils.py:172), entries [i][j] = sum_k Q[k][i] R[k][j]; only the trace and the skew part are used
+        const float tr0 = Q[0] * R[0] + Q[3] * R[3] + Q[6] * R[6];
+        const float tr1 = Q[1] * R[1] + Q[4] * R[4] + Q[7] * R[7];
+        const float tr2 = Q[2] * R[2] + Q[5] * R[5] + Q[8] * R[8];
+        const float e21 = Q[2] * R[1] + Q[5] * R[4] + Q[8] * R[7], e12 = Q[1] * R[2] + Q[4] * R[5] + Q[7] * R[8];
+        const float e02 = Q[0] * R[2] + Q[3] * R[5] + Q[6] * R[8], e20 = Q[2] * R[0] + Q[5] * R[3] + Q[8] * R[6];
+        const float e10 = Q[1] * R[0] + Q[4] * R[3] + Q[7] * R[6], e01 = Q[0] * R[1] + Q[3] * R[4] + Q[6] * R[7];
+        float tr = tr0 + tr1 + tr2;
         tr = fminf(fmaxf(tr, -1.f + 1e-6f), 3.f - 1e-6f);
         const float c = (tr - 1.f) / 2.f;
         const float theta = acosf(c);
         const float den = fmaxf(2.f * sqrtf((1.f - c) * (1.f + c)), 1e-6f);
-        const float k = theta / den;
-        const float wv[3] = {k * (E[7] - E[5]), k * (E[2] - E[6]), k * (E[3] - E[1])};
+        const float kk = theta / den;
+        const int dofs = p.diff_off[m] + jn * 3;
+        __half* o = s_out + f * p.D16 + p.diff_off16[m] + jn * 3;
+        o[0] = __float2half_rn(nz(kk * (e21 - e12), dofs));
+        o[1] = __float2half_rn(nz(kk * (e02 - e20), dofs + 1));
+        o[2] = __float2half_rn(nz(kk * (e10 - e01), dofs + 2));
+      }
+    }
+    __syncthreads();                                   // row norms visible
+
+    // ================= phase B: all warps =================
+    // ---- z-scored raw columns of the non-cosine modalities: 32 columns per job, all frames
+    for (int j = warp; j < pl.n_raw; j += 8) {
+      const int m = pl.raw_mod[j];
+      const int c = pl.raw_col[j] + lane;
+      if (c < p.raw_dim[m]) {
+        const int ro = p.raw_off[m] + c;
+        const float sc = nz.scale ? __ldg(nz.scale + ro) : 1.f, sh = nz.scale ? __ldg(nz.shift + ro) : 0.f;
+        const float* x = s_in + pl.base_off[m] + pl.pitch[m] + c;
+        __half* o = s_out + p.raw_off16[m] + c;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) s_out[f * p.D16 + do16 + jn * 3 + q] = __float2half_rn(nz(wv[q], dofs + jn * 3 + q));
+        for (int f = 0; f < kS; ++f)
+          if (f < nf) o[f * p.D16] = __float2half_rn(fmaf(x[f * pl.pitch[m]], sc, sh));
       }
-    } else if (kind == TAG_KIND_PLAIN) {
-      for (int i = lane; warp < nf && i < dim; i += 32) {      // warp = frame, lane = column
-        const int f = warp;
-        const float d = xin[(f + 1) * in_floats_per_row + i] - xin[f * in_floats_per_row + i];
-        s_out[f * p.D16 + do16 + i] = __float2half_rn(nz(d, dofs + i));
+    }
+    // ---- plain first differences (utils.py:161-163)
+    for (int j = warp; j < pl.n_plain; j += 8) {
+      const int m = pl.plain_mod[j];
+      const int c = pl.plain_col[j] + lane;
+      if (c < p.raw_dim[m]) {
+        const int dofs = p.diff_off[m] + c;
+        const float sc = nz.scale ? __ldg(nz.scale + dofs) : 1.f, sh = nz.scale ? __ldg(nz.shift + dofs) : 0.f;
+        const float* x = s_in + pl.base_off[m] + c;
+        __half* o = s_out + p.diff_off16[m] + c;
+        float prev = x[k0 * pl.pitch[m]];
+#pragma unroll
+        for (int f = 0; f < kS; ++f) {
+          if (f < nf) {
+            const float cur = x[(f + 1) * pl.pitch[m]];
+            o[f * p.D16] = __float2half_rn(fmaf(cur - prev, sc, sh));
+            prev = cur;
+          }
+        }
       }
-    } else if (warp < nf) {  // TAG_KIND_PROCRUSTES: warp f aligns frame t0+f-1 -> t0+f
-      const int f = warp, t = t0 + f;
-      const float* xc = xin + (f + 1) * in_floats_per_row;
-      const float* xp = xin + f * in_floats_per_row;
-      __half* o16 = s_out + f * p.D16;
-      const int K = dim / 2;
-      const int k0 = lane, k1 = lane + 32;
-      const bool a0 = k0 < K, a1 = k1 < K;
-      // centre + Frobenius-normalise one frame's points (utils.py:192-196)
-      auto load_norm = [&](const float* x, float& x0, float& y0, float& x1, float& y1) {
-        x0 = a0 ? x[2 * k0] : 0.f; y0 = a0 ? x[2 * k0 + 1] : 0.f;
-        x1 = a1 ? x[2 * k1] : 0.f; y1 = a1 ? x[2 * k1 + 1] : 0.f;
-        const float mx = warp_sum(x0 + x1) / (float)K, my = warp_sum(y0 + y1) / (float)K;
-        x0 = a0 ? x0 - mx : 0.f; y0 = a0 ? y0 - my : 0.f;
-        x1 = a1 ? x1 - mx : 0.f; y1 = a1 ? y1 - my : 0.f;
-        const float isc = 1.0f / fmaxf(sqrtf(warp_sum(x0 * x0 + y0 * y0 + x1 * x1 + y1 * y1)), 1e-6f);
-        x0 *= isc; y0 *= isc; x1 *= isc; y1 *= isc;
-      };
-      float x0, y0, x1, y1, px0, py0, px1, py1;
-      load_norm(xc, x0, y0, x1, y1);
-      load_norm(xp, px0, py0, px1, py1);
-      float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-      if (t > 0) {
-        // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
-        const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
-        const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
-        if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
-        // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
-        const float ry = h10 - h01, rx = h00 + h11;
-        const float rr = ry * ry + rx * rx;
-        const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
-        const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
-        d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
-        d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
-      }
-      if (a0) {
-        o16[do16 + 2 * k0] = __float2half_rn(nz(d00, dofs + 2 * k0));
-        o16[do16 + 2 * k0 + 1] = __float2half_rn(nz(d01, dofs + 2 * k0 + 1));
-      }
-      if (a1) {
-        o16[do16 + 2 * k1] = __float2half_rn(nz(d10, dofs + 2 * k1));
-        o16[do16 + 2 * k1 + 1] = __float2half_rn(nz(d11, dofs + 2 * k1 + 1));
+    }
+    // ---- cosine modalities, 4 columns per thread
+#pragma unroll 1
+    for (int q = 0; q < pl.n_cos; ++q) {
+      const int m = pl.cos_mod[q];
+      const int dim = p.raw_dim[m];
+      const float* xin = s_in + pl.base_off[m];
+      const int pitch = pl.pitch[m];
+      const int ro = p.raw_off[m], dofs = p.diff_off[m];
+      const bool has_diff = p.diff_dim[m] > 0;
+      const float* invm = s_inv + q * (kS + 1);
+      float inv[kS + 1];
+#pragma unroll
+      for (int k = 0; k <= kS; ++k) inv[k] = invm[k <= nf ? k : 0];
+      for (int i = 4 * tid; i < dim; i += 1024) {
+        float4 sr = make_float4(1.f, 1.f, 1.f, 1.f), hr = make_float4(0.f, 0.f, 0.f, 0.f), sd = sr, hd = hr;
+        if (nz.scale != nullptr) {                      // ro, dofs even on this path (checked on the host): 8-byte loads
+          auto ld4 = [](const float* t) {
+            const float2 a = __ldg(reinterpret_cast<const float2*>(t)), b = __ldg(reinterpret_cast<const float2*>(t + 2));
+            return make_float4(a.x, a.y, b.x, b.y);
+          };
+          sr = ld4(nz.scale + ro + i); hr = ld4(nz.shift + ro + i);
+          if (has_diff) { sd = ld4(nz.scale + dofs + i); hd = ld4(nz.shift + dofs + i); }
+        }
+        float4 prev = *reinterpret_cast<const float4*>(xin + k0 * pitch + i);
+        const float inv0 = k0 ? inv[1] : inv[0];
+        prev.x *= inv0; prev.y *= inv0; prev.z *= inv0; prev.w *= inv0;
+        __half* oraw = s_out + p.raw_off16[m] + i;
+        __half* odif = s_out + p.diff_off16[m] + i;
+#pragma unroll
+        for (int f = 0; f < kS; ++f) {
+          if (f < nf) {
+            const float4 a = *reinterpret_cast<const float4*>(xin + (f + 1) * pitch + i);
+            const __half2 r0 = __floats2half2_rn(fmaf(a.x, sr.x, hr.x), fmaf(a.y, sr.y, hr.y));
+            const __half2 r1 = __floats2half2_rn(fmaf(a.z, sr.z, hr.z), fmaf(a.w, sr.w, hr.w));
+            *reinterpret_cast<uint2*>(oraw + f * p.D16) = make_uint2(*reinterpret_cast<const uint32_t*>(&r0), *reinterpret_cast<const uint32_t*>(&r1));
+            if (has_diff) {
+              const float4 cur = make_float4(a.x * inv[f + 1], a.y * inv[f + 1], a.z * inv[f + 1], a.w * inv[f + 1]);
+              const __half2 d0 = __floats2half2_rn(fmaf(cur.x - prev.x, sd.x, hd.x), fmaf(cur.y - prev.y, sd.y, hd.y));
+              const __half2 d1 = __floats2half2_rn(fmaf(cur.z - prev.z, sd.z, hd.z), fmaf(cur.w - prev.w, sd.w, hd.w));
+              *reinterpret_cast<uint2*>(odif + f * p.D16) = make_uint2(*reinterpret_cast<const uint32_t*>(&d0), *reinterpret_cast<const uint32_t*>(&d1));
+              prev = cur;
+            }
+          }
+        }
       }
     }
   }
@@ -534,29 +584,70 @@ cudaError_t launch_zscore_table(const float* mean, const float* stdv, float* sca
 cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
   if (p.n_windows <= 0) return cudaSuccess;
   if (p.feats == nullptr && p.feats16 != nullptr) {
-    // staged (bulk-copy) kernel for the tensor-core path, when the rows are 16-byte friendly and the tile fits in smem
-    bool ok = true;
-    int in_floats = 0;
-    for (int m = 0; m < p.M; ++m) {
-      if (p.kind[m] == TAG_KIND_COSINE && ((p.raw_dim[m] % 4) != 0 || (p.raw_off[m] & 1) || (p.diff_off[m] & 1))) ok = false;
-      if (reinterpret_cast<uintptr_t>(p.src[m]) & 15) ok = false;
-      in_floats += (p.raw_dim[m] + 3) & ~3;
-    }
+    // staged (bulk-copy) kernel for the tensor-core path, when the layout is 16-byte friendly and the tile fits in smem
     constexpr int kS = kStagedFrames;
-    const int smem_in = ((kS + 1) * in_floats * 4 + 127) & ~127;
-    const int smem_total = smem_in + kS * p.D16 * 2 + (TAG_MAX_MODALITIES * (kS + 1) + 2) * 4 + 16;
-    if (ok && smem_total <= 227 * 1024 && (reinterpret_cast<uintptr_t>(p.feats16) & 15) == 0) {
-      static int configured = 0;
-      if (configured < smem_total) {
-        cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
-        if (e != cudaSuccess) return e;
-        configured = smem_total;
+    StagedPlan pl{};
+    bool ok = (reinterpret_cast<uintptr_t>(p.feats16) & 15) == 0 && (p.D16 % 8) == 0 && p.n_windows * ((p.T + kS - 1) / kS) < (1ll << 31);
+    int wide = 0, compact = 0;
+    for (int m = 0; m < p.M && ok; ++m) {
+      const int dim = p.raw_dim[m];
+      const bool aligned = (dim % 4) == 0 && (reinterpret_cast<uintptr_t>(p.src[m]) & 15) == 0;
+      pl.bulk[m] = aligned ? 1 : 0;
+      if (reinterpret_cast<uintptr_t>(p.src[m]) & 3) ok = false;
+      switch (p.kind[m]) {
+        case TAG_KIND_COSINE:
+          if (!aligned || (p.raw_off[m] & 1) || (p.diff_off[m] & 1) || (p.raw_off16[m] & 3) || (p.diff_off16[m] & 3)) ok = false;
+          pl.cos_mod[pl.n_cos++] = (unsigned char)m;
+          break;
+        case TAG_KIND_ROTMAT:
+          for (int j = 0; j < dim / 9; ++j) {
+            if (pl.n_rot >= kMaxRotItems || j > 255) { ok = false; break; }
+            pl.rot_mod[pl.n_rot] = (unsigned char)m; pl.rot_joint[pl.n_rot++] = (unsigned char)j;
+          }
+          break;
+        case TAG_KIND_PLAIN:
+          for (int c = 0; c < dim; c += 32) {
+            if (pl.n_plain >= kMaxPlainChunks) { ok = false; break; }
+            pl.plain_mod[pl.n_plain] = (unsigned char)m; pl.plain_col[pl.n_plain++] = (short)c;
+          }
+          break;
+        default:  // TAG_KIND_PROCRUSTES: 2-D points, two per lane, half2 stores
+          if (dim > 128 || (dim & 1) || (p.diff_off16[m] & 1) || !aligned) ok = false;
+          pl.proc_mod[pl.n_proc++] = (unsigned char)m;
+          break;
       }
-      const int64_t blocks = p.n_windows * ((p.T + kS - 1) / kS);
-      static int dbg = -1;
-      if (dbg < 0) { const char* e = getenv("TAG_K1_DEBUG"); dbg = e ? atoi(e) : 0; }   // bottleneck experiments only
-      k_feature_fuse_staged<kS><<<(unsigned)blocks, 256, smem_total, s>>>(p, in_floats, smem_in, dbg);
-      return cudaGetLastError();
+      if (p.kind[m] != TAG_KIND_COSINE)
+        for (int c = 0; c < dim; c += 32) {
+          if (pl.n_raw >= kMaxRawChunks || dim > 32000) { ok = false; break; }
+          pl.raw_mod[pl.n_raw] = (unsigned char)m; pl.raw_col[pl.n_raw++] = (short)c;
+        }
+      if (aligned) wide += dim; else compact += ((kS + 1) * dim + 3) & ~3;
+    }
+    if (ok) {
+      pl.wide_pitch = wide;
+      int wo = 0, co = (kS + 1) * wide;
+      for (int m = 0; m < p.M; ++m) {
+        if (pl.bulk[m]) { pl.base_off[m] = wo; pl.pitch[m] = wide; wo += p.raw_dim[m]; }
+        else { pl.base_off[m] = co; pl.pitch[m] = p.raw_dim[m]; co += ((kS + 1) * p.raw_dim[m] + 3) & ~3; }
+      }
+      pl.bpw = (p.T + kS - 1) / kS;
+      pl.out_off = (co * 4 + 127) & ~127;
+      pl.inv_off = pl.out_off + kS * p.D16 * 2;
+      pl.bar_off = (pl.inv_off + TAG_MAX_MODALITIES * (kS + 1) * 4 + 15) & ~15;
+      const int smem_total = pl.bar_off + 16;
+      if (smem_total <= 227 * 1024) {
+        static int configured = 0;
+        if (configured < smem_total) {
+          cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+          if (e != cudaSuccess) return e;
+          configured = smem_total;
+        }
+        const int64_t blocks = p.n_windows * pl.bpw;
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("TAG_K1_DEBUG"); dbg = e ? atoi(e) : 0; }   // bottleneck experiments only
+        k_feature_fuse_staged<kS><<<(unsigned)blocks, 256, smem_total, s>>>(p, pl, dbg);
+        return cudaGetLastError();
+      }
     }
   }
   bool any_cos = false, any_small = false;

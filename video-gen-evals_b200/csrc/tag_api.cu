@@ -688,6 +688,28 @@ int tag_feature_fuse(tag_handle* h, const tag_videos* vids, const float* mean, c
   return TAG_OK;
 }
 
+int tag_debug_feature_fuse16(tag_handle* h, const tag_videos* vids, const float* mean, const float* stdv,
+                             const int32_t* win_video, const int32_t* win_start, int64_t n_windows, int32_t T,
+                             void* feats16_out, int32_t* d16_out, int32_t* flags_out, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  if (d16_out) *d16_out = h->D16;
+  if (!feats16_out) return TAG_OK;
+  if (n_windows < 0 || T < 1) return fail(h, TAG_ERR_INVALID, "n_windows=%lld T=%d", (long long)n_windows, T);
+  if (n_windows == 0) return TAG_OK;
+  if (!win_video || !win_start) return fail(h, TAG_ERR_INVALID, "tag_debug_feature_fuse16: NULL argument");
+  FuseParams p;
+  int rc = fill_fuse_params(h, &p, vids, mean, stdv, win_video, win_start, n_windows, T);
+  if (rc) return rc;
+  p.feats = nullptr; p.feats16 = reinterpret_cast<__half*>(feats16_out); p.flags = flags_out;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  // the generic kernel leaves pad columns untouched (the encoder's own buffer is zeroed once at allocation)
+  CUDA_TRY(h, cudaMemsetAsync(feats16_out, 0, (size_t)n_windows * T * h->D16 * sizeof(__half), (cudaStream_t)stream));
+  if (mean) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
+  LAUNCH_TRY(h, launch_feature_fuse(p, (cudaStream_t)stream));
+  h->launches += feature_fuse_launches(p) - 1;
+  return TAG_OK;
+}
+
 int tag_encode(tag_handle* h, const float* feats, int64_t n_windows, int32_t T, float* seq_embed, float* frame_embeds,
                float* tokens, float* tc_window, void* stream) {
   int rc = check_common(h, n_windows, T);
