@@ -47,6 +47,7 @@ __global__ void k_zscore_table(const float* __restrict__ mean, const float* __re
                                float* __restrict__ shift, int D) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < D) {
+    if (mean == nullptr) { scale[i] = 1.f; shift[i] = 0.f; return; }     // stats=None path: x*1+0 == x exactly
     const float sc = 1.0f / (stdv[i] + kEpsStd);
     scale[i] = sc;
     shift[i] = -mean[i] * sc;
@@ -292,25 +293,30 @@ struct StagedPlan {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int kS>
+template <int kS, bool FULL>
 __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p, const StagedPlan pl, int dbg) {
   extern __shared__ __align__(128) unsigned char sm_raw[];
   float* s_in = reinterpret_cast<float*>(sm_raw);
   __half* s_out = reinterpret_cast<__half*>(sm_raw + pl.out_off);                  // [kS][D16]
   float* s_inv = reinterpret_cast<float*>(sm_raw + pl.inv_off);                    // [n_cos][kS+1]
+  int* s_cofs = reinterpret_cast<int*>(s_inv + TAG_MAX_MODALITIES * (kS + 1));     // [M] float offset of slot 0 (this CTA)
   const uint32_t bar = smem_addr(sm_raw + pl.bar_off);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned w = blockIdx.x / (unsigned)pl.bpw;
   const int t0 = (int)(blockIdx.x - w * (unsigned)pl.bpw) * kS;
-  const int nf = min(kS, p.T - t0);
+  const int nf = FULL ? kS : min(kS, p.T - t0);      // FULL: T is a multiple of kS
   const int vid = p.win_video[w];
   const int start = p.win_start[w];
+  const int64_t n_rows = *p.total_frames;
   const int64_t f0 = p.frame_offset[vid];
   const int L = (int)(p.frame_offset[vid + 1] - f0);
   const int k0 = t0 == 0 ? 1 : 0;                    // slot 0 (= the frame before the window) duplicates slot 1
-  // slots k0..nf are consecutive source frames unless the window is padded (utils.py:371-381)
+  // slots k0..nf are consecutive source frames unless the window is padded (utils.py:371-381); `flat`: the compact
+  // modalities of this block can be fetched as ONE 16-byte-aligned bulk range each (a few floats of the neighbouring
+  // rows ride along on both sides, so the very last rows of the arrays take the scalar path instead)
   const bool consec = start >= 0 && start + t0 + nf - 1 <= L - 1;
+  const bool flat = consec && f0 + start + t0 + nf + 4 <= n_rows;
   auto row_of_slot = [&](int k) -> int64_t { const int t = t0 - 1 + k; return f0 + src_frame(start, t < 0 ? 0 : t, L); };
 
   if (tid == 0) {
@@ -325,14 +331,35 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   }
   __syncthreads();
 
-  // ---- load phase
+  // ---- load phase: warp 0 plans (lane m = modality m) and issues every bulk copy
   if (warp == 0) {
-    uint32_t tx = 0;
-    if (!(dbg & 4))
-      for (int m = 0; m < p.M; ++m) if (pl.bulk[m]) tx += (uint32_t)((nf + 1) * p.raw_dim[m] * 4);
+    uint32_t my_tx = 0, cnt = 0;
+    int64_t gi = 0;
+    bool my_flat = false;
+    if (lane < p.M) {
+      const int dim = p.raw_dim[lane];
+      if (pl.bulk[lane]) {
+        my_tx = (uint32_t)((nf + 1) * dim * 4);
+        s_cofs[lane] = pl.base_off[lane];
+      } else {
+        gi = (f0 + start + t0 - 1 + k0) * (int64_t)dim;          // first float of slot k0
+        const int sh = (int)(gi & 3);
+        cnt = (uint32_t)((sh + (nf + 1 - k0) * dim + 3) & ~3);
+        my_flat = flat;
+        if (my_flat) { my_tx = cnt * 4u; s_cofs[lane] = pl.base_off[lane] + sh - k0 * dim; gi -= sh; }
+        else s_cofs[lane] = pl.base_off[lane];
+      }
+    }
+    if (dbg & 4) { my_tx = 0; my_flat = false; }
+    const uint32_t tx = __reduce_add_sync(FULL_MASK, my_tx);
     if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
     __syncwarp();
-    if (lane <= nf && !(dbg & 4)) {                   // lane k issues the bulk copies of slot k
+    if (my_flat) {
+      const uint32_t d = smem_addr(s_in + pl.base_off[lane]);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(d), "l"(p.src[lane] + gi), "r"(cnt * 4u), "r"(bar) : "memory");
+    }
+    if (lane <= nf && !(dbg & 4)) {                   // lane k issues the per-row bulk copies of slot k
       const int64_t r = row_of_slot(lane);
       for (int m = 0; m < p.M; ++m) {
         if (!pl.bulk[m]) continue;
@@ -344,23 +371,15 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
       }
     }
   }
-  if (!(dbg & 4)) {
+  if (!flat && !(dbg & 4)) {                          // padded windows / last rows of the arrays: slot by slot, scalar
 #pragma unroll 1
     for (int m = 0; m < p.M; ++m) {
       if (pl.bulk[m]) continue;
       const int dim = p.raw_dim[m];
       float* dst = s_in + pl.base_off[m];
-      if (consec) {                                   // one flat coalesced range
-        const float* g = p.src[m] + (f0 + start + t0 - 1 + k0) * dim;
-        const int n = (nf + 1 - k0) * dim;
-        dst += k0 * dim;
-#pragma unroll 4
-        for (int i = tid; i < n; i += 256) dst[i] = __ldg(g + i);
-      } else {
-        for (int k = k0; k <= nf; ++k) {
-          const float* g = p.src[m] + row_of_slot(k) * dim;
-          for (int i = tid; i < dim; i += 256) dst[k * dim + i] = __ldg(g + i);
-        }
+      for (int k = k0; k <= nf; ++k) {
+        const float* g = p.src[m] + row_of_slot(k) * dim;
+        for (int i = tid; i < dim; i += 256) dst[k * dim + i] = __ldg(g + i);
       }
     }
   }
@@ -382,12 +401,12 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
     if (has_proc && warp < 4) {
       // ---- keypoint Procrustes delta: warp f aligns frame t0+f-1 -> t0+f (utils.py:177-217)
       const int f = warp;
-      if (f < nf) {
+      if (FULL || f < nf) {
         for (int q = 0; q < pl.n_proc; ++q) {
           const int m = pl.proc_mod[q];
           const int dim = p.raw_dim[m];
-          const float* xc = s_in + pl.base_off[m] + (f + 1) * pl.pitch[m];
-          const float* xp = s_in + pl.base_off[m] + ((f == 0 && k0) ? 1 : f) * pl.pitch[m];
+          const float* xc = s_in + s_cofs[m] + (f + 1) * pl.pitch[m];
+          const float* xp = s_in + s_cofs[m] + ((f == 0 && k0) ? 1 : f) * pl.pitch[m];
           __half* o16 = s_out + f * p.D16 + p.diff_off16[m];
           const int dofs = p.diff_off[m];
           const int K = dim / 2;
@@ -440,7 +459,7 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
         const int q = j / (nf + 1), k = j - q * (nf + 1);
         const int m = pl.cos_mod[q];
         const int dim = p.raw_dim[m];
-        const float4* x = reinterpret_cast<const float4*>(s_in + pl.base_off[m] + k * pl.pitch[m]);
+        const float4* x = reinterpret_cast<const float4*>(s_in + s_cofs[m] + k * pl.pitch[m]);
         float ss = 0.f;
         for (int i = lane; i < dim / 4; i += 32) {
           const float4 a = x[i];
@@ -453,8 +472,8 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
       for (int e = aw * 32 + lane; e < nf * pl.n_rot; e += naw * 32) {
         const int f = e / pl.n_rot, it = e - f * pl.n_rot;
         const int m = pl.rot_mod[it], jn = pl.rot_joint[it];
-        const float* xc = s_in + pl.base_off[m] + (f + 1) * pl.pitch[m] + jn * 9;
-        const float* xp = s_in + pl.base_off[m] + ((f == 0 && k0) ? 1 : f) * pl.pitch[m] + jn * 9;
+        const float* xc = s_in + s_cofs[m] + (f + 1) * pl.pitch[m] + jn * 9;
+        const float* xp = s_in + s_cofs[m] + ((f == 0 && k0) ? 1 : f) * pl.pitch[m] + jn * 9;
         float R[9], Q[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) { R[k] = xc[k]; Q[k] = xp[k]; }
@@ -487,12 +506,12 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
       const int c = pl.raw_col[j] + lane;
       if (c < p.raw_dim[m]) {
         const int ro = p.raw_off[m] + c;
-        const float sc = nz.scale ? __ldg(nz.scale + ro) : 1.f, sh = nz.scale ? __ldg(nz.shift + ro) : 0.f;
-        const float* x = s_in + pl.base_off[m] + pl.pitch[m] + c;
+        const float sc = __ldg(nz.scale + ro), sh = __ldg(nz.shift + ro);
+        const float* x = s_in + s_cofs[m] + pl.pitch[m] + c;
         __half* o = s_out + p.raw_off16[m] + c;
 #pragma unroll
         for (int f = 0; f < kS; ++f)
-          if (f < nf) o[f * p.D16] = __float2half_rn(fmaf(x[f * pl.pitch[m]], sc, sh));
+          if (FULL || f < nf) o[f * p.D16] = __float2half_rn(fmaf(x[f * pl.pitch[m]], sc, sh));
       }
     }
     // ---- plain first differences (utils.py:161-163)
@@ -501,13 +520,13 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
       const int c = pl.plain_col[j] + lane;
       if (c < p.raw_dim[m]) {
         const int dofs = p.diff_off[m] + c;
-        const float sc = nz.scale ? __ldg(nz.scale + dofs) : 1.f, sh = nz.scale ? __ldg(nz.shift + dofs) : 0.f;
-        const float* x = s_in + pl.base_off[m] + c;
+        const float sc = __ldg(nz.scale + dofs), sh = __ldg(nz.shift + dofs);
+        const float* x = s_in + s_cofs[m] + c;
         __half* o = s_out + p.diff_off16[m] + c;
         float prev = x[k0 * pl.pitch[m]];
 #pragma unroll
         for (int f = 0; f < kS; ++f) {
-          if (f < nf) {
+          if (FULL || f < nf) {
             const float cur = x[(f + 1) * pl.pitch[m]];
             o[f * p.D16] = __float2half_rn(fmaf(cur - prev, sc, sh));
             prev = cur;
@@ -520,24 +539,21 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
     for (int q = 0; q < pl.n_cos; ++q) {
       const int m = pl.cos_mod[q];
       const int dim = p.raw_dim[m];
-      const float* xin = s_in + pl.base_off[m];
+      const float* xin = s_in + s_cofs[m];
       const int pitch = pl.pitch[m];
       const int ro = p.raw_off[m], dofs = p.diff_off[m];
-      const bool has_diff = p.diff_dim[m] > 0;
       const float* invm = s_inv + q * (kS + 1);
       float inv[kS + 1];
 #pragma unroll
-      for (int k = 0; k <= kS; ++k) inv[k] = invm[k <= nf ? k : 0];
+      for (int k = 0; k <= kS; ++k) inv[k] = invm[(FULL || k <= nf) ? k : 0];
       for (int i = 4 * tid; i < dim; i += 1024) {
-        float4 sr = make_float4(1.f, 1.f, 1.f, 1.f), hr = make_float4(0.f, 0.f, 0.f, 0.f), sd = sr, hd = hr;
-        if (nz.scale != nullptr) {                      // ro, dofs even on this path (checked on the host): 8-byte loads
-          auto ld4 = [](const float* t) {
-            const float2 a = __ldg(reinterpret_cast<const float2*>(t)), b = __ldg(reinterpret_cast<const float2*>(t + 2));
-            return make_float4(a.x, a.y, b.x, b.y);
-          };
-          sr = ld4(nz.scale + ro + i); hr = ld4(nz.shift + ro + i);
-          if (has_diff) { sd = ld4(nz.scale + dofs + i); hd = ld4(nz.shift + dofs + i); }
-        }
+        // ro, dofs even on this path (checked on the host): 8-byte table loads
+        auto ld4 = [](const float* t) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(t)), b = __ldg(reinterpret_cast<const float2*>(t + 2));
+          return make_float4(a.x, a.y, b.x, b.y);
+        };
+        const float4 sr = ld4(nz.scale + ro + i), hr = ld4(nz.shift + ro + i);
+        const float4 sd = ld4(nz.scale + dofs + i), hd = ld4(nz.shift + dofs + i);
         float4 prev = *reinterpret_cast<const float4*>(xin + k0 * pitch + i);
         const float inv0 = k0 ? inv[1] : inv[0];
         prev.x *= inv0; prev.y *= inv0; prev.z *= inv0; prev.w *= inv0;
@@ -545,12 +561,12 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
         __half* odif = s_out + p.diff_off16[m] + i;
 #pragma unroll
         for (int f = 0; f < kS; ++f) {
-          if (f < nf) {
+          if (FULL || f < nf) {
             const float4 a = *reinterpret_cast<const float4*>(xin + (f + 1) * pitch + i);
             const __half2 r0 = __floats2half2_rn(fmaf(a.x, sr.x, hr.x), fmaf(a.y, sr.y, hr.y));
             const __half2 r1 = __floats2half2_rn(fmaf(a.z, sr.z, hr.z), fmaf(a.w, sr.w, hr.w));
             *reinterpret_cast<uint2*>(oraw + f * p.D16) = make_uint2(*reinterpret_cast<const uint32_t*>(&r0), *reinterpret_cast<const uint32_t*>(&r1));
-            if (has_diff) {
+            {
               const float4 cur = make_float4(a.x * inv[f + 1], a.y * inv[f + 1], a.z * inv[f + 1], a.w * inv[f + 1]);
               const __half2 d0 = __floats2half2_rn(fmaf(cur.x - prev.x, sd.x, hd.x), fmaf(cur.y - prev.y, sd.y, hd.y));
               const __half2 d1 = __floats2half2_rn(fmaf(cur.z - prev.z, sd.z, hd.z), fmaf(cur.w - prev.w, sd.w, hd.w));
@@ -587,16 +603,16 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
     // staged (bulk-copy) kernel for the tensor-core path, when the layout is 16-byte friendly and the tile fits in smem
     constexpr int kS = kStagedFrames;
     StagedPlan pl{};
-    bool ok = (reinterpret_cast<uintptr_t>(p.feats16) & 15) == 0 && (p.D16 % 8) == 0 && p.n_windows * ((p.T + kS - 1) / kS) < (1ll << 31);
+    bool ok = p.mean != nullptr && p.stdv != nullptr && p.total_frames != nullptr && (reinterpret_cast<uintptr_t>(p.feats16) & 15) == 0 && (p.D16 % 8) == 0 && p.n_windows * ((p.T + kS - 1) / kS) < (1ll << 31);
     int wide = 0, compact = 0;
     for (int m = 0; m < p.M && ok; ++m) {
       const int dim = p.raw_dim[m];
       const bool aligned = (dim % 4) == 0 && (reinterpret_cast<uintptr_t>(p.src[m]) & 15) == 0;
       pl.bulk[m] = aligned ? 1 : 0;
-      if (reinterpret_cast<uintptr_t>(p.src[m]) & 3) ok = false;
+      if (reinterpret_cast<uintptr_t>(p.src[m]) & 15) ok = false;          // bulk copies start at 16-byte boundaries of the array
       switch (p.kind[m]) {
         case TAG_KIND_COSINE:
-          if (!aligned || (p.raw_off[m] & 1) || (p.diff_off[m] & 1) || (p.raw_off16[m] & 3) || (p.diff_off16[m] & 3)) ok = false;
+          if (!aligned || p.diff_dim[m] != dim || (p.raw_off[m] & 1) || (p.diff_off[m] & 1) || (p.raw_off16[m] & 3) || (p.diff_off16[m] & 3)) ok = false;
           pl.cos_mod[pl.n_cos++] = (unsigned char)m;
           break;
         case TAG_KIND_ROTMAT:
@@ -621,31 +637,33 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
           if (pl.n_raw >= kMaxRawChunks || dim > 32000) { ok = false; break; }
           pl.raw_mod[pl.n_raw] = (unsigned char)m; pl.raw_col[pl.n_raw++] = (short)c;
         }
-      if (aligned) wide += dim; else compact += ((kS + 1) * dim + 3) & ~3;
+      if (aligned) wide += dim; else compact += ((kS + 1) * dim + 7) & ~3;
     }
     if (ok) {
       pl.wide_pitch = wide;
       int wo = 0, co = (kS + 1) * wide;
       for (int m = 0; m < p.M; ++m) {
         if (pl.bulk[m]) { pl.base_off[m] = wo; pl.pitch[m] = wide; wo += p.raw_dim[m]; }
-        else { pl.base_off[m] = co; pl.pitch[m] = p.raw_dim[m]; co += ((kS + 1) * p.raw_dim[m] + 3) & ~3; }
+        else { pl.base_off[m] = co; pl.pitch[m] = p.raw_dim[m]; co += ((kS + 1) * p.raw_dim[m] + 7) & ~3; }   // + alignment slack of the flat copy
       }
       pl.bpw = (p.T + kS - 1) / kS;
       pl.out_off = (co * 4 + 127) & ~127;
       pl.inv_off = pl.out_off + kS * p.D16 * 2;
-      pl.bar_off = (pl.inv_off + TAG_MAX_MODALITIES * (kS + 1) * 4 + 15) & ~15;
+      pl.bar_off = (pl.inv_off + TAG_MAX_MODALITIES * (kS + 1) * 4 + TAG_MAX_MODALITIES * 4 + 15) & ~15;
       const int smem_total = pl.bar_off + 16;
       if (smem_total <= 227 * 1024) {
         static int configured = 0;
         if (configured < smem_total) {
-          cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+          cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged<kS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+          if (e == cudaSuccess) e = cudaFuncSetAttribute(k_feature_fuse_staged<kS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
           if (e != cudaSuccess) return e;
           configured = smem_total;
         }
         const int64_t blocks = p.n_windows * pl.bpw;
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("TAG_K1_DEBUG"); dbg = e ? atoi(e) : 0; }   // bottleneck experiments only
-        k_feature_fuse_staged<kS><<<(unsigned)blocks, 256, smem_total, s>>>(p, pl, dbg);
+        if (p.T % kS == 0) k_feature_fuse_staged<kS, true><<<(unsigned)blocks, 256, smem_total, s>>>(p, pl, dbg);
+        else k_feature_fuse_staged<kS, false><<<(unsigned)blocks, 256, smem_total, s>>>(p, pl, dbg);
         return cudaGetLastError();
       }
     }

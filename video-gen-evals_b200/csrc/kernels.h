@@ -14,8 +14,9 @@ struct FuseParams {
   int raw_off16[TAG_MAX_MODALITIES], diff_off16[TAG_MAX_MODALITIES];   // padded fp16 operand columns
   const float* src[TAG_MAX_MODALITIES];
   const int64_t* frame_offset;
-  const float* mean;        // [D] z-score SCALE table 1/(std+1e-6) (launch_zscore_table), or null
-  const float* stdv;        // [D] z-score SHIFT table -mean*scale, or null
+  const int64_t* total_frames;   // &frame_offset[V]: rows of every source array
+  const float* mean;        // [D] z-score SCALE table 1/(std+1e-6) (launch_zscore_table; all ones without stats)
+  const float* stdv;        // [D] z-score SHIFT table -mean*scale (zeros without stats)
   const int32_t* win_video;
   const int32_t* win_start;
   int64_t n_windows;

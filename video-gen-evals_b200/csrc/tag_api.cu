@@ -445,8 +445,9 @@ int fill_fuse_params(tag_handle* h, FuseParams* p, const tag_videos* vids, const
   }
   if (n_proc > 1) return fail(h, TAG_ERR_UNSUPPORTED, "at most one TAG_KIND_PROCRUSTES modality is supported");
   p->frame_offset = vids->frame_offset;
-  p->mean = mean ? h->zs_scale : nullptr;      // the kernel reads the (scale, shift) tables
-  p->stdv = mean ? h->zs_shift : nullptr;
+  p->mean = h->zs_scale;                       // the kernel reads the (scale, shift) tables (identity without stats)
+  p->stdv = h->zs_shift;
+  p->total_frames = vids->frame_offset + vids->n_videos;
   p->win_video = win_video; p->win_start = win_start; p->n_windows = n; p->T = T; p->D = h->D; p->D16 = h->D16;
   return TAG_OK;
 }
@@ -682,7 +683,7 @@ int tag_feature_fuse(tag_handle* h, const tag_videos* vids, const float* mean, c
   if (rc) return rc;
   p.feats = feats_out; p.feats16 = nullptr; p.flags = flags_out;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  if (mean) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
+  LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
   LAUNCH_TRY(h, launch_feature_fuse(p, (cudaStream_t)stream));
   h->launches += feature_fuse_launches(p) - 1;
   return TAG_OK;
@@ -704,7 +705,7 @@ int tag_debug_feature_fuse16(tag_handle* h, const tag_videos* vids, const float*
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   // the generic kernel leaves pad columns untouched (the encoder's own buffer is zeroed once at allocation)
   CUDA_TRY(h, cudaMemsetAsync(feats16_out, 0, (size_t)n_windows * T * h->D16 * sizeof(__half), (cudaStream_t)stream));
-  if (mean) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
+  LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, (cudaStream_t)stream));
   LAUNCH_TRY(h, launch_feature_fuse(p, (cudaStream_t)stream));
   h->launches += feature_fuse_launches(p) - 1;
   return TAG_OK;
@@ -756,7 +757,7 @@ int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean,
   const bool tc = h->cfg.precision == TAG_PRECISION_FP16_TC;
   prof_begin(h);
   const int S = T + 1;
-  if (mean && stdv) LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, s));
+  LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, s));
   for (int64_t w0 = 0; w0 < n_windows; w0 += h->cfg.max_windows) {
     const int64_t W = (n_windows - w0 < h->cfg.max_windows) ? n_windows - w0 : h->cfg.max_windows;
     FuseParams p;
