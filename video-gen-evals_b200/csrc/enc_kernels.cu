@@ -164,6 +164,99 @@ __global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
   Row8<TA>::store(reinterpret_cast<TA*>(p.mix) + r * kD + lane * 8, mix);
 }
 
+// fp16-activation form of the same step, built for memory-level parallelism: the row's 2*M 16-byte loads per lane are
+// all issued before any arithmetic (the generic kernel above chained load -> three dependent shuffle reductions per
+// modality and sat at 31 % of HBM bandwidth), the shuffle reductions of all modalities run interleaved (two sequences
+// in total instead of three per modality), and kv is never materialised:
+//   logit_m = sc_m * sum_k d_m[k] g[k] qk[k] + sum_k b[k] qk[k],   mix[k] = g[k] * sum_m (a_m sc_m) d_m[k] + b[k]
+// with d_m = s_m - mean_m, sc_m = rstd1 * rstd2 (see above), a = softmax(logit) (sum_m a_m = 1).
+template <int MM>
+__global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
+  const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= p.R) return;
+  uint4 us[MM], um[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    us[m] = make_uint4(0u, 0u, 0u, 0u); um[m] = us[m];
+    if (m < p.M) {
+      us[m] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.ps[m]) + r * kD + lane * 8));
+      if (p.pm[m] != nullptr) um[m] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.pm[m]) + r * kD + lane * 8));
+    }
+  }
+  float g[8], b[8], gq[8];
+  Row8<float>::load(p.kv_gamma + lane * 8, g);
+  Row8<float>::load(p.kv_beta + lane * 8, b);
+  Row8<float>::load(p.qk + lane * 8, gq);
+  float bq = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { bq = fmaf(b[k], gq[k], bq); gq[k] *= g[k]; }
+  float d[MM][8], s1[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const __half2* hs = reinterpret_cast<const __half2*>(&us[m]);
+    const __half2* hm = reinterpret_cast<const __half2*>(&um[m]);
+    s1[m] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(hs[i]), c = __half22float2(hm[i]);
+      d[m][2 * i] = a.x + c.x; d[m][2 * i + 1] = a.y + c.y;            // s = state + motion  (model.py:174)
+      s1[m] += d[m][2 * i] + d[m][2 * i + 1];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int m = 0; m < MM; ++m) s1[m] += __shfl_xor_sync(FULL_MASK, s1[m], o);
+  }
+  bq = warp_sum(bq);
+  float s2[MM], sq[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const float mean = s1[m] * (1.0f / kD);
+    s2[m] = 0.f; sq[m] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { d[m][k] -= mean; s2[m] = fmaf(d[m][k], d[m][k], s2[m]); sq[m] = fmaf(d[m][k], gq[k], sq[m]); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int m = 0; m < MM; ++m) { s2[m] += __shfl_xor_sync(FULL_MASK, s2[m], o); sq[m] += __shfl_xor_sync(FULL_MASK, sq[m], o); }
+  }
+  float logit[MM], sc[MM];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const float var = s2[m] * (1.0f / kD);
+    const float rstd1 = 1.0f / sqrtf(var + kLnEps);
+    const float var_u = var * rstd1 * rstd1;                  // variance of the first LayerNorm's output
+    sc[m] = rstd1 / sqrtf(var_u + kLnEps);
+    logit[m] = -CUDART_INF_F;
+    if (m < p.M) {
+      logit[m] = fmaf(sc[m], sq[m], bq) * p.inv_tau[m] + p.lbias[m];    // Q . (Wk kv) / sqrt(D), model.py:89-91
+      mx = fmaxf(mx, logit[m]);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int m = 0; m < MM; ++m) { logit[m] = (m < p.M) ? expf(logit[m] - mx) : 0.f; den += logit[m]; }
+  const float inv_den = 1.0f / den;
+  float mix[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mix[k] = 0.f;
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const float a = logit[m] * inv_den;
+    const float wgt = a * sc[m];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mix[k] = fmaf(wgt, d[m][k], mix[k]);
+    if (p.attn != nullptr && lane == 0 && m < p.M) p.attn[r * p.M + m] = a;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mix[k] = fmaf(mix[k], g[k], b[k]);
+  Row8<__half>::store(reinterpret_cast<__half*>(p.mix) + r * kD + lane * 8, mix);
+}
+
 // ---------------------------------------------------------------- tokens = [cls ; frames] + PE
 template <typename TA>
 __global__ void __launch_bounds__(256) k_build_tokens(const TA* __restrict__ fused, const float* __restrict__ cls,
@@ -273,13 +366,19 @@ __global__ void __launch_bounds__(640) k_attention(const TA* __restrict__ qkv, T
 }
 
 // ---------------------------------------------------------------- self-attention on mma.sync fragments (S <= 48)
-// One warp per (window, head): Q, K (row-major, padded to 48 x 40 halfs) and V^T (32 x 56 halfs) staged in shared
-// memory, S = Q K^T as 3 x 6 tiles of m16n8k16 (fp16 in, fp32 accumulate), softmax on the accumulator fragments
-// (row statistics via quad shuffles, exp2 domain), P re-used in registers as the A operand of P V (3 x 4 tiles).
+// One warp per (window, head): Q, K, V (row-major, 48 rows x 40 halfs each) are fetched with 16-byte cp.async — all
+// ~400 requests of a warp in flight at once, nothing passes through registers — S = Q K^T as 3 x 6 tiles of m16n8k16
+// (fp16 in, fp32 accumulate), softmax on the accumulator fragments (row statistics via quad shuffles, exp2 domain),
+// P re-used in registers as the A operand of P V (3 x 4 tiles) whose B fragments come from row-major V through
+// ldmatrix.trans; the output tile is staged in shared memory and leaves as 16-byte stores (64 B per row).
 // 72 tensor instructions replace ~4.7k scalar-FMA warp instructions per (window, head). Attention is 0.03 % of the
 // encoder's FLOPs, so the legacy warp-level MMA is the right tool here; the GEMM-shaped 99.9 % runs on tcgen05.
-constexpr int kAttS = 48, kQStride = 40, kVStride = 56;
-constexpr int kAttWarpHalfs = 2 * kAttS * kQStride + 32 * kVStride;      // Q + K + V^T per warp
+constexpr int kAttS = 48, kQStride = 40;
+constexpr int kAttWarpHalfs = 3 * kAttS * kQStride;                      // Q + K + V per warp
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -297,21 +396,20 @@ __global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict_
   const int h = (int)(pair - n * n_heads);
   __half* sQ = smh + (size_t)warp * kAttWarpHalfs;
   __half* sK = sQ + kAttS * kQStride;
-  __half* sVt = sK + kAttS * kQStride;
-  // zero (padding rows / keys must be exact zeros), then fill
-  for (int i = lane; i < kAttWarpHalfs / 8; i += 32) reinterpret_cast<uint4*>(sQ)[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncwarp();
+  __half* sV = sK + kAttS * kQStride;
   const __half* base = qkv + n * (int64_t)S * (3 * kD) + h * 32;
   for (int u = lane; u < S * 4; u += 32) {
     const int row = u >> 2, part = u & 3;
     const __half* src = base + (int64_t)row * (3 * kD) + part * 8;
-    *reinterpret_cast<uint4*>(sQ + row * kQStride + part * 8) = __ldg(reinterpret_cast<const uint4*>(src));
-    *reinterpret_cast<uint4*>(sK + row * kQStride + part * 8) = __ldg(reinterpret_cast<const uint4*>(src + kD));
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + 2 * kD));
-    const __half* vh = reinterpret_cast<const __half*>(&v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sVt[(part * 8 + e) * kVStride + row] = vh[e];
+    cp_async16(sQ + row * kQStride + part * 8, src);
+    cp_async16(sK + row * kQStride + part * 8, src + kD);
+    cp_async16(sV + row * kQStride + part * 8, src + 2 * kD);
   }
+  // value rows of the padding keys must be exact zeros (P is 0 there, but 0 x NaN would poison the sum); padding rows
+  // of Q / K only produce scores that are masked or rows that are never stored
+  for (int u = lane; u < (kAttS - S) * 4; u += 32)
+    *reinterpret_cast<uint4*>(sV + (S + (u >> 2)) * kQStride + (u & 3) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncwarp();
 
   const int g = lane >> 2, tig = lane & 3;
@@ -395,26 +493,35 @@ __global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict_
 #pragma unroll
   for (int kt = 0; kt < 3; ++kt) {
 #pragma unroll
-    for (int nd = 0; nd < 4; ++nd) {
-      uint32_t bv[2];
-      const __half* vp = sVt + (nd * 8 + g) * kVStride + kt * 16 + 2 * tig;
-      bv[0] = *reinterpret_cast<const uint32_t*>(vp);
-      bv[1] = *reinterpret_cast<const uint32_t*>(vp + 8);
+    for (int np = 0; np < 2; ++np) {                 // two 8-wide d tiles per ldmatrix.x4
+      // matrices: (keys kt*16 + 0..7, d tile 2np), (keys +8..15, d tile 2np), (keys 0..7, d tile 2np+1), (keys +8..15, 2np+1)
+      const int mi = lane >> 3, rr = lane & 7;
+      const __half* vp = sV + (kt * 16 + (mi & 1) * 8 + rr) * kQStride + (2 * np + (mi >> 1)) * 8;
+      uint32_t b0, b1, b2, b3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"((uint32_t)__cvta_generic_to_shared(vp)));
+      const uint32_t bva[2] = {b0, b1}, bvb[2] = {b2, b3};
 #pragma unroll
-      for (int mt = 0; mt < 3; ++mt) mma_16816(o[mt][nd], pa[mt][kt], bv);
+      for (int mt = 0; mt < 3; ++mt) { mma_16816(o[mt][2 * np], pa[mt][kt], bva); mma_16816(o[mt][2 * np + 1], pa[mt][kt], bvb); }
     }
   }
-  // ---- store rows < S
-  __half* ob = out + n * (int64_t)S * kD + h * 32;
+  // ---- output: stage the [48 x 32] tile over Q (dead after the score MMAs), then 16 bytes per lane, 64 B per row
+  __syncwarp();
 #pragma unroll
   for (int mt = 0; mt < 3; ++mt) {
     const int r0 = mt * 16 + g, r1 = r0 + 8;
 #pragma unroll
     for (int nd = 0; nd < 4; ++nd) {
       const int col = nd * 8 + 2 * tig;
-      if (r0 < S) *reinterpret_cast<__half2*>(ob + (int64_t)r0 * kD + col) = __floats2half2_rn(o[mt][nd][0] * inv_sum[mt][0], o[mt][nd][1] * inv_sum[mt][0]);
-      if (r1 < S) *reinterpret_cast<__half2*>(ob + (int64_t)r1 * kD + col) = __floats2half2_rn(o[mt][nd][2] * inv_sum[mt][1], o[mt][nd][3] * inv_sum[mt][1]);
+      *reinterpret_cast<__half2*>(sQ + r0 * kQStride + col) = __floats2half2_rn(o[mt][nd][0] * inv_sum[mt][0], o[mt][nd][1] * inv_sum[mt][0]);
+      *reinterpret_cast<__half2*>(sQ + r1 * kQStride + col) = __floats2half2_rn(o[mt][nd][2] * inv_sum[mt][1], o[mt][nd][3] * inv_sum[mt][1]);
     }
+  }
+  __syncwarp();
+  __half* ob = out + n * (int64_t)S * kD + h * 32;
+  for (int u = lane; u < S * 4; u += 32) {
+    const int row = u >> 2, part = u & 3;
+    *reinterpret_cast<uint4*>(ob + (int64_t)row * kD + part * 8) = *reinterpret_cast<const uint4*>(sQ + row * kQStride + part * 8);
   }
 }
 
@@ -490,7 +597,13 @@ template cudaError_t launch_groupnorm<__half>(const __half*, const float*, const
 template <typename TA>
 cudaError_t launch_merge_fusion(const MergeParams& p, cudaStream_t s) {
   if (p.R <= 0) return cudaSuccess;
-  k_merge_fusion<TA><<<(unsigned)((p.R + 7) / 8), 256, 0, s>>>(p);
+  const unsigned grid = (unsigned)((p.R + 7) / 8);
+  if constexpr (sizeof(TA) == 2) {
+    if (p.M <= 5) k_merge_fusion_h<5><<<grid, 256, 0, s>>>(p);
+    else k_merge_fusion_h<TAG_MAX_MODALITIES><<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+  }
+  k_merge_fusion<TA><<<grid, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 template cudaError_t launch_merge_fusion<float>(const MergeParams&, cudaStream_t);
