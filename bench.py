@@ -11,8 +11,9 @@ videos are sharded across ranks with no data-path collective; t
 precedes the timed region is where the one NCCL all-reduce happens.
 
   value  : whole-job videos/s with inputs already resident in HBM (CUDA events, max over ranks)
-  e2e    : same metric through the public API with HOST (pinned) input buffers: H2D of every input
-           array + scoring + D2H of the per-video results inside the timed region
+  e2e    : same metric through the public streaming call (TagScorer.score_stream) with HOST (pinned)
+           input buffers: every step's H2D of all input arrays (copy stream, prefetched across step
+           boundaries) + scoring + D2H of the per-video results, all inside the timed region
   roofline: dominant kernel = the dilated-conv tensor-core GEMM; achieved = algorithmic FLOPs per launch
            / mean launch duration measured with CUDA events on the launching stream during the timed
            steps; peak = MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)
