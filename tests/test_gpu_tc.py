@@ -163,6 +163,28 @@ def test_encoder_tc_vs_fp32_mode_full_batch():
     assert e_seq < 2e-3 and e_tc < 1e-3
 
 
+@pytest.mark.parametrize("T", [8, 16, 64, 128])
+def test_encoder_tc_vs_fp32_mode_other_clip_lengths(T):
+    """Clip lengths other than the goldens' 32 / 256: S = T + 1 = 9, 17 (one-warp attention), 65, 129 (flash-style attention
+    over key chunks), fused GroupNorm with 16 / 8 / 2 / 1 windows per tile. Tensor-core mode vs the fp32 mode of the same
+    library on the same windows (the fp32 mode is pinned to the reference by the golden tests)."""
+    g = golden_case("m5_t32")
+    vb = tb.make_videos(24, T + 5, seed=4242 + T)
+    stats = g.stats()
+    res = {}
+    for prec in ("fp32", "fp16_tc"):
+        model = _model(g, prec, max_windows=32)
+        scorer = tb.TagScorer(model, stats, T, max(1, T // 4), DEV)
+        enc = scorer.encode(scorer.to_device(vb), want_frames=True)
+        res[prec] = (enc["seq"].cpu(), enc["tc_window"].cpu(), enc["frames"].cpu())
+    assert res["fp32"][0].shape[0] >= 24 and res["fp32"][2].shape[1] == T + 1
+    e_seq = max_abs(res["fp32"][0], res["fp16_tc"][0])
+    e_fr = max_abs(res["fp32"][2], res["fp16_tc"][2])
+    e_tc = float(((res["fp32"][1] - res["fp16_tc"][1]).abs() / res["fp32"][1]).max())
+    print(f"T={T}: seq {e_seq:.2e} frames {e_fr:.2e} tc rel {e_tc:.2e}")
+    assert e_seq < 2e-3 and e_fr < 4e-3 and e_tc < 1e-3
+
+
 def test_fused_pipeline_tc_scores():
     g = golden_case("m5_t32")
     model = _model(g, "fp16_tc", max_windows=16)

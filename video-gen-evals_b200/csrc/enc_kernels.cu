@@ -525,6 +525,140 @@ __global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- self-attention, any S > 48 (long clips: S = 65 ... 257 ...)
+// One CTA (4 warps) per (window, head): Q, K, V [S_pad x 40 halfs] of the head are fetched once with cp.async; each warp
+// takes 16-query blocks round-robin and walks the keys in chunks of 32 with an online softmax (flash-attention recurrence in
+// the exp2 domain): 8 score MMAs, rescale, 8 P.V MMAs per chunk, V fragments through ldmatrix.trans. The finished 16 x 32
+// output block is staged over the warp's own (dead) Q rows and leaves as 16-byte stores.
+__global__ void __launch_bounds__(128) k_attention_flash(const __half* __restrict__ qkv, __half* __restrict__ out, int S, int S_pad,
+                                                         int n_heads) {
+  extern __shared__ __align__(16) __half smh[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = blockIdx.x / n_heads;
+  const int h = (int)(blockIdx.x - n * n_heads);
+  __half* sQ = smh;
+  __half* sK = sQ + (size_t)S_pad * kQStride;
+  __half* sV = sK + (size_t)S_pad * kQStride;
+  const __half* base = qkv + n * (int64_t)S * (3 * kD) + h * 32;
+  for (int u = threadIdx.x; u < S * 4; u += 128) {
+    const int row = u >> 2, part = u & 3;
+    const __half* src = base + (int64_t)row * (3 * kD) + part * 8;
+    cp_async16(sQ + row * kQStride + part * 8, src);
+    cp_async16(sK + row * kQStride + part * 8, src + kD);
+    cp_async16(sV + row * kQStride + part * 8, src + 2 * kD);
+  }
+  // padding rows: V must be exact zeros (P = 0 there, but 0 x NaN poisons the sum); Q / K zeroed too so that masked scores
+  // and never-stored rows stay finite
+  for (int u = threadIdx.x; u < (S_pad - S) * 4; u += 128) {
+    const int off = (S + (u >> 2)) * kQStride + (u & 3) * 8;
+    *reinterpret_cast<uint4*>(sQ + off) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sK + off) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sV + off) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int g = lane >> 2, tig = lane & 3;
+  const float scale = 0.17677669529663688110f * 1.4426950408889634f;      // log2(e) / sqrt(32)
+  __half* ob = out + n * (int64_t)S * kD + h * 32;
+  for (int qb = warp; qb * 16 < S; qb += 4) {
+    uint32_t aq[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const __half* qp = sQ + (qb * 16 + g) * kQStride + ks * 16 + 2 * tig;
+      aq[ks][0] = *reinterpret_cast<const uint32_t*>(qp);
+      aq[ks][1] = *reinterpret_cast<const uint32_t*>(qp + 8 * kQStride);
+      aq[ks][2] = *reinterpret_cast<const uint32_t*>(qp + 8);
+      aq[ks][3] = *reinterpret_cast<const uint32_t*>(qp + 8 * kQStride + 8);
+    }
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+    float o[4][4];
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[nd][e] = 0.f;
+    for (int kc = 0; kc < S_pad; kc += 32) {
+      float sc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          uint32_t bk[2];
+          const __half* kp = sK + (kc + nt * 8 + g) * kQStride + ks * 16 + 2 * tig;
+          bk[0] = *reinterpret_cast<const uint32_t*>(kp);
+          bk[1] = *reinterpret_cast<const uint32_t*>(kp + 8);
+          mma_16816(sc[nt], aq[ks], bk);
+        }
+      }
+      float mx0 = m0, mx1 = m1;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int c0 = kc + nt * 8 + 2 * tig;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[nt][e] = (c0 + (e & 1) < S) ? sc[nt][e] * scale : -CUDART_INF_F;
+        mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 2));
+      // every chunk holds at least one real key (S_pad - S < 32), so mx is finite from the first chunk on
+      const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);
+      m0 = mx0; m1 = mx1;
+      l0 *= a0; l1 *= a1;
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) { o[nd][0] *= a0; o[nd][1] *= a0; o[nd][2] *= a1; o[nd][3] *= a1; }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        sc[nt][0] = exp2f(sc[nt][0] - mx0); sc[nt][1] = exp2f(sc[nt][1] - mx0);
+        sc[nt][2] = exp2f(sc[nt][2] - mx1); sc[nt][3] = exp2f(sc[nt][3] - mx1);
+        l0 += sc[nt][0] + sc[nt][1];
+        l1 += sc[nt][2] + sc[nt][3];
+      }
+#pragma unroll
+      for (int kt = 0; kt < 2; ++kt) {
+        uint32_t pa[4];
+        __half2 t;
+        t = __floats2half2_rn(sc[2 * kt][0], sc[2 * kt][1]);         pa[0] = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(sc[2 * kt][2], sc[2 * kt][3]);         pa[1] = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(sc[2 * kt + 1][0], sc[2 * kt + 1][1]); pa[2] = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2half2_rn(sc[2 * kt + 1][2], sc[2 * kt + 1][3]); pa[3] = *reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          const int mi = lane >> 3, rr = lane & 7;
+          const __half* vp = sV + (kc + kt * 16 + (mi & 1) * 8 + rr) * kQStride + (2 * np + (mi >> 1)) * 8;
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"((uint32_t)__cvta_generic_to_shared(vp)));
+          const uint32_t bva[2] = {b0, b1}, bvb[2] = {b2, b3};
+          mma_16816(o[2 * np], pa, bva);
+          mma_16816(o[2 * np + 1], pa, bvb);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(FULL_MASK, l0, 1); l0 += __shfl_xor_sync(FULL_MASK, l0, 2);
+    l1 += __shfl_xor_sync(FULL_MASK, l1, 1); l1 += __shfl_xor_sync(FULL_MASK, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    // stage over this warp's own Q rows (their A fragments are in registers), then 16 bytes per lane
+    __syncwarp();
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {
+      const int col = nd * 8 + 2 * tig;
+      *reinterpret_cast<__half2*>(sQ + (qb * 16 + g) * kQStride + col) = __floats2half2_rn(o[nd][0] * i0, o[nd][1] * i0);
+      *reinterpret_cast<__half2*>(sQ + (qb * 16 + g + 8) * kQStride + col) = __floats2half2_rn(o[nd][2] * i1, o[nd][3] * i1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = lane; u < 64; u += 32) {
+      const int row = qb * 16 + (u >> 2), part = u & 3;
+      if (row < S) *reinterpret_cast<uint4*>(ob + (int64_t)row * kD + part * 8) = *reinterpret_cast<const uint4*>(sQ + row * kQStride + part * 8);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- LayerNorm with affine
 template <typename TA>
 __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -645,6 +779,18 @@ cudaError_t launch_attention(const TA* qkv, TA* out, int64_t n_windows, int S, i
   if (n_windows <= 0) return cudaSuccess;
   if constexpr (sizeof(TA) == 2) {
     if (S <= kAttS) return launch_attention_mma(qkv, out, n_windows, S, n_heads, s);
+    const int S_pad = (S + 31) / 32 * 32;
+    const size_t smem = (size_t)3 * S_pad * kQStride * sizeof(__half);
+    if (smem <= 200 * 1024 && n_windows * n_heads < (1ll << 31)) {
+      static size_t configured = 48 * 1024;
+      if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_attention_flash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+      }
+      k_attention_flash<<<(unsigned)(n_windows * n_heads), 128, smem, s>>>(qkv, out, S, S_pad, n_heads);
+      return cudaGetLastError();
+    }
   }
   // largest head group whose K/V fit comfortably in shared memory
   auto fits = [&](int hpc) { return n_heads % hpc == 0 && (size_t)2 * S * hpc * kHeadPad * sizeof(float) <= 160 * 1024; };
