@@ -112,6 +112,40 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_cpus(index):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index` (NUMA locality of the pinned staging
+    buffers of the end-to-end leg). Returns a short description, or None when NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs local to GPU {phys}"
+    except Exception:
+        pass
+    return None
+
+
+def h2d_bandwidth(torch, dev, nbytes=1 << 30):
+    """Measured pinned host -> device copy rate on this box (explains the e2e/value gap)."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return 3 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_pass(pkg, n_videos, frames, seed, sd, dims_raw, dims_diff, ostats, centroids):
     """The reference's CPU compute path (oracle port): window features -> encoder -> AC + TC for n_videos
@@ -190,6 +224,8 @@ def main():
         raise RuntimeError("bench.py needs a CUDA (B200) device")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_cpus(local_rank)      # pinned host buffers are then first-touched on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -284,6 +320,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.videos * e2e_steps / (float(t.item()) / 1000.0)
+    h2d_gbs = h2d_bandwidth(torch, dev)
+    for tid in os.listdir("/proc/self/task"):   # the CPU baseline below uses every host core, on every thread
+        try:
+            os.sched_setaffinity(int(tid), all_cpus)
+        except OSError:
+            pass
     assert float((hac - ac.cpu()).abs().max()) < 1e-5
 
     if rank == 0:
@@ -319,8 +361,8 @@ def main():
                                               "frac": (k1_bytes / (k1_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if k1_ms > 0 else None},
                          "whole_encoder_tflops": value / world * (n_windows / args.videos) * GFLOP_PER_WINDOW / 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(2 * args.videos * 4),
-                    "steps": e2e_steps, "call": "TagScorer.score_stream: every step's 5 input arrays copied from pinned host memory "
-                    "(2 blocks per step, prefetched on a copy stream), per-video AC/TC read back to the host every step"},
+                    "steps": e2e_steps, "h2d_gbs_measured": h2d_gbs, "host_affinity": numa, "call": "TagScorer.score_stream: every step's 5 input arrays copied from pinned host memory "
+                    "(one block per encoder pass, short ramp-up blocks at the start of the stream, prefetched on a copy stream), per-video AC/TC read back to the host every step"},
             "gpu_launches": l1 - l0,
             "clocks": clocks,
         }

@@ -228,7 +228,7 @@ def test_score_stream_matches_resident_scores():
     for hb in host:
         a, t = scorer.score(scorer.to_device(hb.to(DEV)), cen)
         want.append((a.cpu(), t.cpu()))
-    for pieces, prefetch in ((1, 0), (2, 2), (3, 1), (7, 4)):
+    for pieces, prefetch in ((None, 3), (1, 0), (2, 2), (3, 1), (7, 4)):
         got = list(scorer.score_stream(iter(host), cen, pieces=pieces, prefetch=prefetch))
         assert len(got) == len(host)
         for (ga, gt), (wa, wt) in zip(got, want):

@@ -18,7 +18,7 @@ Wt = (torch.randn(N, 5 * K, device=DEV, generator=g) / math.sqrt(5 * K)).half()
 R16 = torch.randn(M, N, device=DEV, generator=g).half()
 C16 = torch.empty(M, N, device=DEV, dtype=torch.float16)
 gam, bet = torch.ones(N, device=DEV), torch.zeros(N, device=DEV)
-print("env: HALO=%s PAIR=%s DEBUG=%s" % (os.environ.get("TAG_TC_HALO", "1"), os.environ.get("TAG_TC_PAIR", "1"), os.environ.get("TAG_TC_DEBUG", "0")))
+print("env: HALO=%s PAIR=%s DEBUG=%s" % (os.environ.get("TAG_TC_HALO", "0"), os.environ.get("TAG_TC_PAIR", "1"), os.environ.get("TAG_TC_DEBUG", "0")))
 for dil in (1, 2, 4, 8):
     for name, res, gn in (("conv1 gelu", None, False), ("conv2+GN", R16, True)):
         def run():

@@ -46,16 +46,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // MUFU rcp/ex2 — ~16 instructions per element instead of erff's ~30, which is what lets the epilogue warps keep
 // pace with the MMA pipe (budget: 40 thread-instructions per output element at K = 1280).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
+  // GELU(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2), erfc(u) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-u^2),
+  // t = 1 / (1 + 0.3275911 u). With z = |x| sqrt(log2(e) / 2): exp(-u^2) = 2^(-z^2), so the exponent needs no extra scaling.
+  constexpr float kZ = 0.84932180028801904272f;              // sqrt(log2(e) / 2)
+  constexpr float kT = 0.3275911f * 0.70710678118654752440f / kZ;   // 0.3275911 u = kT z
+  constexpr float kH = 0.5f / kZ;                            // 0.5 |x| = kH z
+  const float z = fabsf(x) * kZ;
   float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(kT, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -z));
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
   p = fmaf(t, p, 0.254829592f);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);            // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  return fmaf(-kH * (p * t), z * e, fmaxf(x, 0.0f));
 }
 
 // activation storage type helpers: the encoder keeps activations as float (fp32 mode) or

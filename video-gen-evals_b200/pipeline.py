@@ -121,14 +121,34 @@ class TagScorer:
         self.last_flags = enc["flags"]
         return ac, tc
 
-    def score_stream(self, batches, centroids: torch.Tensor, pieces: int = 2, prefetch: int = 2):
+    def _block_plan(self, lengths: Sequence[int], first: bool) -> List[Tuple[int, int]]:
+        """Cut a batch into contiguous blocks of videos for `score_stream` (pieces=None): every block is one encoder
+        pass (<= model.max_windows windows), and the FIRST batch of a stream starts with short blocks (1, 3, 15 GEMM
+        waves) so that only a sliver of host->device copy is exposed before the encoder has work."""
+        seg = window_table(lengths, self.clip_len, self.stride)[2]             # cumulative windows per video
+        T = self.clip_len
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        wave = max(1, (sms // 2) * 256 // T)                                   # windows per wave of the CTA-pair GEMM
+        cap = max(1, int(self.model.max_windows))
+        steps = [wave, 3 * wave, 15 * wave] if first else []
+        blocks, lo, V = [], 0, len(lengths)
+        while lo < V:
+            want = min(steps.pop(0), cap) if steps else cap
+            hi = int(np.searchsorted(seg, seg[lo] + want, side="right")) - 1   # last video that still fits
+            hi = max(hi, lo + 1)
+            blocks.append((lo, min(hi, V)))
+            lo = min(hi, V)
+        return blocks
+
+    def score_stream(self, batches, centroids: torch.Tensor, pieces: Optional[int] = None, prefetch: int = 3):
         """Streaming end-to-end call: `batches` is an iterable of HOST (ideally pinned) VideoBatch objects; yields
         one `(ac [V], tc [V])` pair of CPU tensors per batch, in order. This is the `e2e` leg of bench.py.
 
-        Every batch is cut into `pieces` contiguous blocks of videos. Blocks are copied host->device on a side stream
-        up to `prefetch` blocks ahead of the block being scored (across batch boundaries), and the 8 B/video results
-        go back through a pinned buffer one batch behind the compute, so in steady state the PCIe time (350 KB per
-        video) hides behind the encoder. At most prefetch+2 blocks of inputs are alive on the device."""
+        Every batch is cut into contiguous blocks of videos (`pieces` equal blocks, or — default — one block per
+        encoder pass with a short ramp at the start of the stream, see `_block_plan`). Blocks are copied host->device
+        on a side stream up to `prefetch` blocks ahead of the block being scored (across batch boundaries), and the
+        8 B/video results go back through a pinned buffer one batch behind the compute, so in steady state the PCIe
+        time (350 KB per video) hides behind the encoder. At most prefetch+2 blocks of inputs are alive on the device."""
         from collections import deque
         dev = self.device
         main = torch.cuda.current_stream(dev)
@@ -138,25 +158,32 @@ class TagScorer:
         cs.wait_stream(main)
 
         def jobs():
-            for vb in batches:
-                n = max(1, min(int(pieces), vb.n_videos))
-                for i in range(n):
-                    lo, hi = shard_range(vb.n_videos, i, n)
-                    yield vb, lo, hi, i == n - 1
+            for b, vb in enumerate(batches):
+                if pieces is None:
+                    plan = self._block_plan([vb.length(v) for v in range(vb.n_videos)], first=(b == 0))
+                else:
+                    n = max(1, min(int(pieces), vb.n_videos))
+                    plan = [shard_range(vb.n_videos, i, n) for i in range(n)]
+                cap = max(vb.offsets[hi] - vb.offsets[lo] for lo, hi in plan)     # frames of the largest block
+                for i, (lo, hi) in enumerate(plan):
+                    yield vb, lo, hi, i == len(plan) - 1, cap
 
         it = jobs()
         staged, done = deque(), []
+        # device staging ring: block j lives in slot j % ring_slots, and its copy waits for the block that used the slot
+        # before (done[j - ring_slots]) — no allocator traffic and no cross-stream frees inside the stream
+        ring_slots = prefetch + 2
 
         def stage():
             job = next(it, None)
             if job is None:
                 return
-            vb, lo, hi, last = job
+            vb, lo, hi, last, cap = job
             j = len(done) + len(staged)                       # index of this block in the stream
             if j - prefetch - 2 >= 0:
                 cs.wait_event(done[j - prefetch - 2])         # bound the device copies that are alive
             with torch.cuda.stream(cs):
-                piece = vb.slice(lo, hi).to(dev)
+                piece = self._stage_block(vb.slice(lo, hi), j % ring_slots, cap)
                 ev = torch.cuda.Event()
                 ev.record(cs)
             staged.append((vb, lo, hi, last, piece, ev))
@@ -173,9 +200,6 @@ class TagScorer:
         while staged:
             vb, lo, hi, last, piece, ev = staged.popleft()
             main.wait_event(ev)
-            for t in (piece.pose, piece.gori, piece.betas, piece.vit, piece.kp, piece.clip, piece.dino):
-                if t is not None:
-                    t.record_stream(main)
             if lo == 0:
                 out = torch.empty(2, vb.n_videos, device=dev, dtype=torch.float32)
                 flags = None
@@ -197,6 +221,26 @@ class TagScorer:
                 pending = (e, host, flags)
         if pending is not None:
             yield finish(pending)
+
+    def _stage_block(self, hb: VideoBatch, slot: int, cap_frames: int) -> VideoBatch:
+        """Copy a host block into staging slot `slot` (device buffers of at least `cap_frames` frames, re-allocated only
+        when a larger batch plan arrives) on the current stream; returns a VideoBatch of views."""
+        ring = self.__dict__.setdefault("_ring", {})
+        bufs = ring.setdefault(slot, {})
+        out = {}
+        for name in ("pose", "gori", "betas", "vit", "kp", "clip", "dino"):
+            src = getattr(hb, name)
+            if src is None:
+                out[name] = None
+                continue
+            buf = bufs.get(name)
+            if buf is None or buf.shape[0] < src.shape[0] or buf.shape[1:] != src.shape[1:]:
+                buf = torch.empty((max(int(cap_frames), src.shape[0]),) + tuple(src.shape[1:]), device=self.device, dtype=src.dtype)
+                bufs[name] = buf
+            out[name] = buf[:src.shape[0]]
+            out[name].copy_(src, non_blocking=True)
+        return VideoBatch(out["pose"], out["gori"], out["betas"], out["vit"], out["kp"], list(hb.offsets), list(hb.cls_idx),
+                          list(hb.names), out["clip"], out["dino"], list(hb.classes))
 
     def score_host(self, vb_host: VideoBatch, centroids: torch.Tensor, pieces: int = 4) -> Tuple[torch.Tensor, torch.Tensor]:
         """End-to-end call with HOST buffers for one batch: H2D of every input array, score, D2H of the per-video
