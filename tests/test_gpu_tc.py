@@ -185,6 +185,53 @@ def test_encoder_tc_vs_fp32_mode_other_clip_lengths(T):
     assert e_seq < 2e-3 and e_fr < 4e-3 and e_tc < 1e-3
 
 
+def test_full_size_properties_tc():
+    """One full encoder pass of BASELINE config 2 and a bit (2,700 videos x 64 frames -> 13,500 windows: the 13,024-window
+    pass boundary falls inside the batch) through size-independent properties: per-video scores do not depend on the
+    order of the videos, on the pass size, or on what else is in the batch; duplicated videos score identically; and a
+    sample of the videos agrees with the CPU oracle to the north-star tolerance."""
+    dims_raw, dims_diff = tb.dims_maps(False)
+    sd = tb.make_state_dict(dims_raw, dims_diff, seed=0)
+    real = tb.make_videos(100, 64, seed=1340, device=DEV)
+    stats = tb.compute_stats_from_videos(real, dims_raw, dims_diff, DEV)
+    V = 2700
+    gen = tb.make_videos(V, 64, seed=1339, device=DEV)
+    res = {}
+    for mw in (13024, 4096):
+        model = tb.HumanActionScorer(dims_raw, dims_diff, precision="fp16_tc", max_windows=mw)
+        model.load_state_dict(sd)
+        model.to(DEV).eval()
+        scorer = tb.TagScorer(model, stats, 32, 8, DEV)
+        if mw == 13024:
+            cen, cnt = scorer.build_centroids(scorer.to_device(real), 10)
+            assert float(cnt.sum()) == 100 * 5
+        ac, tc = scorer.score(scorer.to_device(gen), cen)
+        res[mw] = (ac.cpu(), tc.cpu())
+        assert int(scorer.last_flags.item()) == 0
+    ac, tc = res[13024]
+    assert bool(torch.isfinite(ac).all()) and bool(torch.isfinite(tc).all())
+    assert float(ac.min()) > 0 and float(ac.max()) < 2.0 and float(tc.min()) > 0
+    # pass size: rows are processed independently, so the split into passes must not change a single bit
+    assert torch.equal(res[4096][0], ac) and torch.equal(res[4096][1], tc)
+    # order + batch composition + duplicates: reversed order, every 9th video, and video 7 three times
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(V, generator=g).tolist()
+    sub = perm[::9] + [7, 7, 7]
+    ac2, tc2 = scorer.score(scorer.to_device(gen.select(sub)), cen)
+    assert torch.equal(ac2.cpu(), ac[sub]) and torch.equal(tc2.cpu(), tc[sub])
+    # a sample against the oracle (fp32 CPU restatement of the reference)
+    pick = [0, 1234, V - 1]
+    host = gen.select(pick).to("cpu")
+    ostats = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in (stats if isinstance(stats, dict) else vars(stats)).items()}
+    label_dict = {c: i for i, c in enumerate(tb.ACTION_CLASSES)}
+    oac, otc, _ = O.score_videos([host.video(i) for i in range(len(pick))], host.names, [host.cls_name(i) for i in range(len(pick))],
+                                 sd, dims_raw, dims_diff, ostats, cen.cpu(), label_dict, clip_len=32, stride=8)
+    for i, v in enumerate(pick):
+        key = host.names[i].rsplit(".", 1)[0]
+        assert abs(oac[key] - float(ac[v])) / oac[key] < 1e-3, (v, oac[key], float(ac[v]))
+        assert abs(otc[key] - float(tc[v])) / otc[key] < 1e-3, (v, otc[key], float(tc[v]))
+
+
 def test_fused_pipeline_tc_scores():
     g = golden_case("m5_t32")
     model = _model(g, "fp16_tc", max_windows=16)
