@@ -284,7 +284,7 @@ struct StagedPlan {
   int pitch[TAG_MAX_MODALITIES];             // floats between its slots (wide_pitch, or dim when compact)
   unsigned char bulk[TAG_MAX_MODALITIES];    // 1: one cp.async.bulk per slot
   int n_raw, n_plain, n_rot, n_proc, n_cos;
-  unsigned char raw_mod[kMaxRawChunks];   short raw_col[kMaxRawChunks];      // z-scored raw copies, 32 columns per chunk
+  unsigned char raw_mod[kMaxRawChunks];   short raw_col[kMaxRawChunks];      // z-scored raw copies, 64 columns per chunk
   unsigned char plain_mod[kMaxPlainChunks]; short plain_col[kMaxPlainChunks];
   unsigned char rot_mod[kMaxRotItems];    unsigned char rot_joint[kMaxRotItems];
   unsigned char proc_mod[TAG_MAX_MODALITIES];
@@ -319,20 +319,14 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
   const bool flat = consec && f0 + start + t0 + nf + 4 <= n_rows;
   auto row_of_slot = [&](int k) -> int64_t { const int t = t0 - 1 + k; return f0 + src_frame(start, t < 0 ? 0 : t, L); };
 
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  {  // zero the output tile (pad columns stay zero)
-    uint4* z = reinterpret_cast<uint4*>(s_out);
-    const int n16 = kS * p.D16 / 8;
-#pragma unroll 2
-    for (int i = tid; i < n16; i += 256) z[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
-  __syncthreads();
-
-  // ---- load phase: warp 0 plans (lane m = modality m) and issues every bulk copy
+  // ---- load phase: warp 0 alone owns the mbarrier (init, expect_tx, wait), plans (lane m = modality m) and issues every
+  // bulk copy; the other warps go straight to zeroing the output tile, which overlaps the copies' flight time
   if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     uint32_t my_tx = 0, cnt = 0;
     int64_t gi = 0;
     bool my_flat = false;
@@ -370,6 +364,12 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
                      ::"r"(d), "l"(g), "r"((uint32_t)(dim * 4)), "r"(bar) : "memory");
       }
     }
+  }
+  {  // zero the output tile (pad columns stay zero); ordered before the phase A/B writes by the barrier below
+    uint4* z = reinterpret_cast<uint4*>(s_out);
+    const int n16 = kS * p.D16 / 8;
+#pragma unroll 2
+    for (int i = tid; i < n16; i += 256) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   if (!flat && !(dbg & 4)) {                          // padded windows / last rows of the arrays: slot by slot, scalar
 #pragma unroll 1
@@ -500,18 +500,26 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
     __syncthreads();                                   // row norms visible
 
     // ================= phase B: all warps =================
-    // ---- z-scored raw columns of the non-cosine modalities: 32 columns per job, all frames
+    // ---- z-scored raw columns of the non-cosine modalities: 64 columns per job (two per lane, one half2 store), all frames
     for (int j = warp; j < pl.n_raw; j += 8) {
       const int m = pl.raw_mod[j];
-      const int c = pl.raw_col[j] + lane;
-      if (c < p.raw_dim[m]) {
+      const int c = pl.raw_col[j] + 2 * lane;
+      const int dim = p.raw_dim[m];
+      if (c < dim) {
+        const bool two = c + 1 < dim;
         const int ro = p.raw_off[m] + c;
-        const float sc = __ldg(nz.scale + ro), sh = __ldg(nz.shift + ro);
-        const float* x = s_in + s_cofs[m] + pl.pitch[m] + c;
-        __half* o = s_out + p.raw_off16[m] + c;
+        const float sc0 = __ldg(nz.scale + ro), sh0 = __ldg(nz.shift + ro);
+        const float sc1 = two ? __ldg(nz.scale + ro + 1) : 0.f, sh1 = two ? __ldg(nz.shift + ro + 1) : 0.f;
+        const int pitch = pl.pitch[m];
+        const float* x = s_in + s_cofs[m] + pitch + c;
+        __half* o = s_out + p.raw_off16[m] + c;                 // even column of a 64-aligned block: 4-byte aligned
 #pragma unroll
-        for (int f = 0; f < kS; ++f)
-          if (FULL || f < nf) o[f * p.D16] = __float2half_rn(fmaf(x[f * pl.pitch[m]], sc, sh));
+        for (int f = 0; f < kS; ++f) {
+          if (FULL || f < nf) {
+            const float x0 = x[f * pitch], x1 = two ? x[f * pitch + 1] : 0.f;   // the odd tail column is a zero pad column
+            *reinterpret_cast<__half2*>(o + f * p.D16) = __floats2half2_rn(fmaf(x0, sc0, sh0), fmaf(x1, sc1, sh1));
+          }
+        }
       }
     }
     // ---- plain first differences (utils.py:161-163)
@@ -610,6 +618,7 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
       const bool aligned = (dim % 4) == 0 && (reinterpret_cast<uintptr_t>(p.src[m]) & 15) == 0;
       pl.bulk[m] = aligned ? 1 : 0;
       if (reinterpret_cast<uintptr_t>(p.src[m]) & 15) ok = false;          // bulk copies start at 16-byte boundaries of the array
+      if ((p.raw_off16[m] & 1) || (p.diff_off16[m] & 1)) ok = false;       // half2 stores
       switch (p.kind[m]) {
         case TAG_KIND_COSINE:
           if (!aligned || p.diff_dim[m] != dim || (p.raw_off[m] & 1) || (p.diff_off[m] & 1) || (p.raw_off16[m] & 3) || (p.diff_off16[m] & 3)) ok = false;
@@ -633,7 +642,7 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
           break;
       }
       if (p.kind[m] != TAG_KIND_COSINE)
-        for (int c = 0; c < dim; c += 32) {
+        for (int c = 0; c < dim; c += 64) {
           if (pl.n_raw >= kMaxRawChunks || dim > 32000) { ok = false; break; }
           pl.raw_mod[pl.n_raw] = (unsigned char)m; pl.raw_col[pl.n_raw++] = (short)c;
         }
