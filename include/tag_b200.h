@@ -112,6 +112,15 @@ int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean,
                        float* seq_embed, float* frame_embeds, float* tokens, float* tc_window,
                        int32_t* flags_out, void* stream);
 
+/* --- the same for clips of EQUAL length: every video has exactly L frames (frame_offset[v+1] - frame_offset[v] == L) and the
+ *     windows are the reference's regular grid, starts 0, stride, 2*stride, ... <= L - T (eval.py:358-359 with
+ *     WindowDataset utils.py:343-365), window-major by video: n_windows = n_videos * ((L - T) / stride + 1). Equivalent to
+ *     tag_encode_windows on that window table. In tensor-core mode with T a power of two in 16..128 the library builds the
+ *     features ONCE PER SOURCE FRAME (overlapping windows share frames) and lets the stem GEMMs gather the windows. */
+int tag_encode_clips(tag_handle* h, const tag_videos* vids, const float* mean, const float* stdv, int64_t n_videos,
+                     int32_t L, int32_t T, int32_t stride, float* seq_embed, float* frame_embeds, float* tokens,
+                     float* tc_window, int32_t* flags_out, void* stream);
+
 /* --- K3 centroids: build_train_centroids_subset (utils.py:1035-1043).
  *     sums_counts [C, 257] (256 sums || count) is accumulated INTO (zero it first); it is the
  *     buffer that is all-reduced across ranks before tag_centroid_finalize. labels int32 [n];

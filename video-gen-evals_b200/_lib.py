@@ -61,6 +61,7 @@ SIGNATURES = {
     "tag_set_profiling": (C.c_int, [_P, _I32]),
     "tag_get_profile": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "tag_debug_gemm_f32": (C.c_int, [_P, _P, _I32, _P, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P]),
+    "tag_encode_clips": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "tag_debug_feature_fuse16": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "tag_debug_gemm_tc": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
 }

@@ -76,7 +76,8 @@ struct TcParams {
   int N;
   int kb_per_tap;       // K / 64
   int taps, dil;
-  int mode;             // 0 plain rows, 1 conv with T <= 128 (tile = 128/T windows), 2 conv with T % 128 == 0
+  int mode;             // 0 plain rows, 1 conv with T <= 128 (tile = 128/T windows), 2 conv with T % 128 == 0,
+                        // 3 plain GEMM whose rows are gathered window by window from a per-frame table
   int T, wpt, tpw;      // frames per window, windows per tile (mode 1), tiles per window (mode 2)
   int64_t m_tiles;
   int n_tiles;
@@ -96,6 +97,8 @@ struct TcParams {
   int a_stage_bytes;       // bytes of one staged A chunk (multiple of 1024); two A stages
   int a_box_bytes;         // bytes the TMA box delivers (zero-filled rows included)
   int b_stages;            // weight-tile stages behind the two A stages
+  int g_L, g_wpv, g_stride;   // mode 3: frames per clip, windows per clip, window stride (frames)
+  const float* row0_vec;      // fp16-out path: rows with (row % T) == 0 take this [N] vector
   int tap_rows;            // dil * NW: shared-memory rows between consecutive taps
   int lw, lt;              // log2(windows per tile), log2(frames per window): tile row r <-> window r & (NW-1), frame r >> lw
 };
@@ -443,6 +446,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int64_t m_tile = m_tile_of(tile);
         const int n_tile = (int)(tile % p.n_tiles);
         int c1_base, c2;
+        int grow[8];                                            // mode 3: table row of each window of the tile
+        if (p.mode == 3) {
+          c1_base = 0; c2 = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t w = m_tile * p.wpt + i;
+            const int64_t v = w / p.g_wpv;
+            grow[i] = (int)(v * p.g_L + (w - v * p.g_wpv) * p.g_stride);
+          }
+        } else
         if (p.mode == 0) { c1_base = (int)(m_tile * BLOCK_M); c2 = 0; }
         else if (p.mode == 1) { c1_base = 0; c2 = (int)(m_tile * p.wpt); }
         else { c2 = (int)(m_tile / p.tpw); c1_base = (int)(m_tile - (int64_t)c2 * p.tpw) * BLOCK_M; }
@@ -455,10 +468,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const uint32_t tx = (ld_a ? A_BYTES : 0) + (ld_b ? Cfg<PAIR>::B_BYTES : 0);
           if constexpr (PAIR) {
             if (leader) { if (tx) mbar_arrive_expect_tx(full_bar(stage), 2 * tx); else mbar_arrive(full_bar(stage)); }   // bytes of both CTAs
+            if (ld_a && p.mode == 3) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.wpt) tma_load_3d_pair(sa + (uint32_t)(i * p.T) * 128u, &map_a, full_bar(stage), kc * BLOCK_K, grow[i], 0);
+            } else
             if (ld_a) tma_load_3d_pair(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
             if (ld_b) tma_load_2d_pair(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
           } else {
             if (tx) mbar_arrive_expect_tx(full_bar(stage), tx); else mbar_arrive(full_bar(stage));
+            if (ld_a && p.mode == 3) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.wpt) tma_load_3d(sa + (uint32_t)(i * p.T) * 128u, &map_a, full_bar(stage), kc * BLOCK_K, grow[i], 0);
+            } else
             if (ld_a) tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
             if (ld_b) tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
           }
@@ -731,6 +754,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       } else if (!out32) {
         // ---- fp16 output (optional fp16 residual): 2 units of 32 columns
         const bool has_res = p.res16 != nullptr;
+        const bool row_is_t0 = p.row0_vec != nullptr && ((tile_row(rm.tile_base, rm.rt0 + lane, rm.lw, rm.lt) & (int64_t)(p.T - 1)) == 0);
         uint4 rres[4];
         if (has_res) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
         mbar_wait(tfull_bar(acc), acc_phase);
@@ -751,6 +775,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             float v[CW];
             if (has_res) epi_values<16>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
             else epi_values<0>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+            if (row_is_t0) {                                   // first frame of a window: the fixed zero-motion row
+#pragma unroll
+              for (int i = 0; i < CW; i += 4) {
+                const float4 z = __ldg(reinterpret_cast<const float4*>(p.row0_vec + n_base + c * CW + i));
+                v[i] = z.x; v[i + 1] = z.y; v[i + 2] = z.z; v[i + 3] = z.w;
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint4 o;
@@ -959,11 +990,25 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     }
     gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)g.T; gdim[2] = (cuuint64_t)W;
     gstr[0] = (cuuint64_t)g.lda * 2; gstr[1] = (cuuint64_t)g.T * g.lda * 2;
+  } else if (g.g_L > 0) {
+    if (g.T < 16 || g.T > BLOCK_M || (g.T & (g.T - 1)) || g.M % g.T || g.g_wpv < 1 || g.g_stride < 1 || g.g_rows < g.T ||
+        g.g_rows >= (1ll << 31) || g.gn_gamma != nullptr || ln)
+      return bad("window gather needs a plain GEMM with T a power of two in 16..128");
+    p.mode = 3; p.wpt = BLOCK_M / g.T; p.tpw = 1;
+    p.g_L = g.g_L; p.g_wpv = g.g_wpv; p.g_stride = g.g_stride;
+    box[0] = BLOCK_K; box[1] = (cuuint32_t)g.T; box[2] = 1;
+    gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)g.g_rows; gdim[2] = 1;
+    gstr[0] = (cuuint64_t)g.lda * 2; gstr[1] = (cuuint64_t)g.g_rows * g.lda * 2;
   } else {
     p.mode = 0; p.wpt = 1; p.tpw = 1;
     box[0] = BLOCK_K; box[1] = BLOCK_M; box[2] = 1;
     gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)g.M; gdim[2] = 1;
     gstr[0] = (cuuint64_t)g.lda * 2; gstr[1] = (cuuint64_t)g.M * g.lda * 2;
+  }
+  if (g.row0_vec != nullptr) {
+    if (g.C16 == nullptr || g.T < 1 || (g.T & (g.T - 1)) || g.gn_gamma != nullptr || ln || (reinterpret_cast<uintptr_t>(g.row0_vec) & 15))
+      return bad("row0_vec needs an fp16-output plain epilogue and T a power of two");
+    p.row0_vec = g.row0_vec;
   }
   CUtensorMap map_a, map_b;
   CUresult r = ctx->encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(g.A), gdim, gstr, box, estr,

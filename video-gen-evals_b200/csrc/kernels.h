@@ -116,6 +116,12 @@ struct GemmTC {
   const float* gn_beta;
   const float* ln_gamma;          // non-null: fuse LayerNorm over the 256 output columns after bias + fp32 residual;
   const float* ln_beta;           //   needs N == 256, res32, C32 (may alias res32) and C16
+  // window gather (the stems in frame-table mode): A is a per-FRAME table [g_rows, lda] of clips of g_L frames each, and
+  // logical row (window w, frame t) reads table row (w / g_wpv) * g_L + (w % g_wpv) * g_stride + t. Plain GEMM, T a power of
+  // two in 16..128. row0_vec non-null: output rows with t == 0 are replaced by this [N] vector (a window's first frame has
+  // zero motion whatever the table holds).
+  int g_L, g_wpv, g_stride; int64_t g_rows;
+  const float* row0_vec;
 };
 struct TcContext;   // opaque: driver entry points + cached tensor maps
 TcContext* tc_context_create(int device, char* err, int errlen);

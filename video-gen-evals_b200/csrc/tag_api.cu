@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "common.cuh"
 #include "kernels.h"
 
 namespace {
@@ -75,6 +76,12 @@ struct tag_handle {
   int* col_tab = nullptr;           // device [M][6] column map fp32 feats -> fp16 operand layout
   float* zs_scale = nullptr;        // [D] z-score tables, rebuilt from (mean, std) at every feature-fuse call
   float* zs_shift = nullptr;
+  // frame-table mode (tag_encode_clips): window index helpers and the motion stems' zero-motion output rows
+  int32_t* iota = nullptr;          // [max_windows] 0, 1, 2, ...
+  int32_t* zeros = nullptr;         // [max_windows] 0
+  int32_t *clip_wv = nullptr, *clip_ws = nullptr;   // [max_windows] window table of one pass (fallback path)
+  float* row0 = nullptr;            // [M][256]: motion stem applied to the z-scored zero difference
+  int frame_table = 1;              // TAG_FRAME_TABLE=0 disables the mode (A/B)
 };
 
 namespace {
@@ -300,8 +307,12 @@ int encode_chunk_f32(tag_handle* h, cudaStream_t s, const float* feats, int64_t 
 }
 
 // ---- tensor-core mode -----------------------------------------------------------------------------
+// frame-table mode: feats16 holds ONE row per source frame of the pass's clips (L rows per clip); windows are gathered by
+// the stem GEMMs (GemmTC::g_*), and the first frame of every window takes the motion stems' zero-motion row
+struct ClipGather { int L = 0, wpv = 0, stride = 0; int64_t rows = 0; };
+
 int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_t W, int T, float* seq, float* frame,
-                    float* tokens, float* tcw) {
+                    float* tokens, float* tcw, const ClipGather* cg = nullptr) {
   const int64_t R = W * T, R2 = W * (T + 1);
   const int M = h->M;
   __half* bufH = (__half*)h->bufH; __half* bufY1 = (__half*)h->bufY1; __half* bufY2 = (__half*)h->bufY2;
@@ -317,6 +328,10 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
       GemmTC g{};
       g.A = feats16 + (side == 0 ? h->raw_off16[m] : h->diff_off16[m]); g.M = R; g.lda = h->D16;
       g.W = e.stem16; g.N = kD; g.K = e.k16; g.taps = 1; g.dil = 1; g.T = T; g.C16 = bufH; g.ldc = kD;
+      if (cg != nullptr) {
+        g.g_L = cg->L; g.g_wpv = cg->wpv; g.g_stride = cg->stride; g.g_rows = cg->rows;
+        if (side == 1) g.row0_vec = h->row0 + (size_t)m * kD;
+      }
       rc = gemm_tc_run(h, s, g, 2.0 * R * kD * e.d_in); if (rc) return rc;
       for (int b = 0; b < h->cfg.n_blocks; ++b) {
         GemmTC c1{};
@@ -425,6 +440,31 @@ int prof_collect(tag_handle* h) {
   }
   h->prof_used = 0;
   return TAG_OK;
+}
+
+// row0[n] = sum_k half(shift[k]) * W16[n][k]: what a motion stem GEMM produces for a row whose z-scored difference is zero
+// (K1 writes half(0 * scale + shift) there); same fp16 operands as the tensor-core GEMM, fp32 accumulation
+__global__ void k_row0_vec(const float* __restrict__ shift, const __half* __restrict__ W16, int k_valid, int k16,
+                           float* __restrict__ out) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= kD) return;
+  float acc = 0.f;
+  for (int k = lane; k < k_valid; k += 32)
+    acc = fmaf(__half2float(__float2half_rn(shift[k])), __half2float(W16[(size_t)n * k16 + k]), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[n] = acc;
+}
+
+__global__ void k_iota_zero(int32_t* iota, int32_t* zeros, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { iota[i] = i; zeros[i] = 0; }
+}
+
+// window table of clips of equal length: window w of the pass = clip v0 + w / wpv, start (w % wpv) * stride
+__global__ void k_clip_windows(int32_t* wv, int32_t* ws, int64_t w0, int n, int wpv, int stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int64_t w = w0 + i; wv[i] = (int32_t)(w / wpv); ws[i] = (int32_t)(w % wpv) * stride; }
 }
 
 int fill_fuse_params(tag_handle* h, FuseParams* p, const tag_videos* vids, const float* mean, const float* stdv,
@@ -664,9 +704,17 @@ int tag_finalize_weights(tag_handle* h) {
       t.push_back(h->diff_off[m]); t.push_back(h->cfg.diff_dims[m]); t.push_back(h->diff_off16[m]);
     }
     if ((rc = upload(h, &h->col_tab, t))) return rc;
+    const int mw = h->cfg.max_windows;
+    if ((rc = dev_alloc(h, &h->iota, mw)) || (rc = dev_alloc(h, &h->zeros, mw)) || (rc = dev_alloc(h, &h->row0, (size_t)h->M * kD))) return rc;
+    k_iota_zero<<<(mw + 255) / 256, 256>>>(h->iota, h->zeros, mw);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    const char* env = getenv("TAG_FRAME_TABLE");
+    if (env != nullptr) h->frame_table = atoi(env);
   } else {
     if ((rc = dev_alloc(h, &h->feats, R * h->D))) return rc;
   }
+  if ((rc = dev_alloc(h, &h->clip_wv, h->cfg.max_windows)) || (rc = dev_alloc(h, &h->clip_ws, h->cfg.max_windows))) return rc;
   h->finalized = true;
   return TAG_OK;
 }
@@ -762,6 +810,79 @@ int tag_encode_windows(tag_handle* h, const tag_videos* vids, const float* mean,
     const int64_t W = (n_windows - w0 < h->cfg.max_windows) ? n_windows - w0 : h->cfg.max_windows;
     FuseParams p;
     rc = fill_fuse_params(h, &p, vids, mean, stdv, win_video + w0, win_start + w0, W, T);
+    if (rc) return rc;
+    p.feats = tc ? nullptr : h->feats;
+    p.feats16 = tc ? h->feats16 : nullptr;
+    p.flags = flags_out;
+    { ProfScope ps(h, s, 3, (double)W * T * ((double)h->raw_total * 4 + (tc ? (double)h->D16 * 2 : (double)h->D * 4))); LAUNCH_TRY(h, launch_feature_fuse(p, s)); h->launches += feature_fuse_launches(p) - 1; }
+    float* seq = seq_embed + w0 * kD;
+    float* fr = frame_embeds ? frame_embeds + w0 * S * kD : nullptr;
+    float* tk = tokens ? tokens + w0 * S * kD : nullptr;
+    float* tw = tc_window ? tc_window + w0 : nullptr;
+    rc = tc ? encode_chunk_tc(h, s, h->feats16, W, T, seq, fr, tk, tw) : encode_chunk_f32(h, s, h->feats, W, T, seq, fr, tk, tw);
+    if (rc) return rc;
+  }
+  return prof_end(h, s);
+}
+
+int tag_encode_clips(tag_handle* h, const tag_videos* vids, const float* mean, const float* stdv, int64_t n_videos,
+                     int32_t L, int32_t T, int32_t stride, float* seq_embed, float* frame_embeds, float* tokens,
+                     float* tc_window, int32_t* flags_out, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  if (n_videos < 0 || L < 1 || T < 1 || stride < 1 || L < T)
+    return fail(h, TAG_ERR_INVALID, "tag_encode_clips: n_videos=%lld L=%d T=%d stride=%d (need L >= T)", (long long)n_videos, L, T, stride);
+  const int wpv = (L - T) / stride + 1;                  // windows per clip: starts 0, stride, ... <= L - T (eval.py:358-359 grid)
+  const int64_t n_windows = n_videos * wpv;
+  int rc = check_common(h, n_windows, T);
+  if (rc) return rc;
+  if (n_windows == 0) return TAG_OK;
+  if (!vids || !vids->frame_offset || !seq_embed) return fail(h, TAG_ERR_INVALID, "tag_encode_clips: NULL argument");
+  if (vids->n_videos < n_videos) return fail(h, TAG_ERR_INVALID, "tag_encode_clips: vids holds %lld videos, %lld requested", (long long)vids->n_videos, (long long)n_videos);
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tc = h->cfg.precision == TAG_PRECISION_FP16_TC;
+  const int S = T + 1;
+  const int64_t cap_rows = (int64_t)h->cfg.max_windows * h->cfg.max_T;        // rows of feats16
+  int64_t vpp = h->cfg.max_windows / wpv;                                    // clips per pass
+  if (vpp > cap_rows / L) vpp = cap_rows / L;
+  const bool frame_mode = tc && h->frame_table && T >= 16 && T <= 128 && (T & (T - 1)) == 0 && vpp >= 1;
+  prof_begin(h);
+  LAUNCH_TRY(h, launch_zscore_table(mean, stdv, h->zs_scale, h->zs_shift, h->D, s));
+  if (frame_mode) {
+    for (int m = 0; m < h->M; ++m) {
+      if (h->cfg.diff_dims[m] <= 0) continue;
+      k_row0_vec<<<kD / 8, 256, 0, s>>>(h->zs_shift + h->diff_off[m], h->motion[m].stem16, h->cfg.diff_dims[m], h->motion[m].k16,
+                                        h->row0 + (size_t)m * kD);
+      h->launches++;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    for (int64_t v0 = 0; v0 < n_videos; v0 += vpp) {
+      const int64_t V = (n_videos - v0 < vpp) ? n_videos - v0 : vpp;
+      const int64_t W = V * wpv, w0 = v0 * wpv;
+      // K1 over whole clips: "window" i = clip v0 + i, start 0, L frames -> one table row per source frame
+      tag_videos sub = *vids;
+      sub.frame_offset = vids->frame_offset + v0;
+      sub.n_videos = vids->n_videos - v0;
+      FuseParams p;
+      rc = fill_fuse_params(h, &p, &sub, mean, stdv, h->iota, h->zeros, V, L);
+      if (rc) return rc;
+      p.feats = nullptr; p.feats16 = h->feats16; p.flags = flags_out;
+      { ProfScope ps(h, s, 3, (double)V * L * ((double)h->raw_total * 4 + (double)h->D16 * 2)); LAUNCH_TRY(h, launch_feature_fuse(p, s)); h->launches += feature_fuse_launches(p) - 1; }
+      ClipGather cg; cg.L = L; cg.wpv = wpv; cg.stride = stride; cg.rows = V * L;
+      rc = encode_chunk_tc(h, s, h->feats16, W, T, seq_embed + w0 * kD, frame_embeds ? frame_embeds + w0 * S * kD : nullptr,
+                           tokens ? tokens + w0 * S * kD : nullptr, tc_window ? tc_window + w0 : nullptr, &cg);
+      if (rc) return rc;
+    }
+    return prof_end(h, s);
+  }
+  // general path: build each pass's window table on the device and run the window pipeline
+  for (int64_t w0 = 0; w0 < n_windows; w0 += h->cfg.max_windows) {
+    const int64_t W = (n_windows - w0 < h->cfg.max_windows) ? n_windows - w0 : h->cfg.max_windows;
+    k_clip_windows<<<(unsigned)((W + 255) / 256), 256, 0, s>>>(h->clip_wv, h->clip_ws, w0, (int)W, wpv, stride);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    FuseParams p;
+    rc = fill_fuse_params(h, &p, vids, mean, stdv, h->clip_wv, h->clip_ws, W, T);
     if (rc) return rc;
     p.feats = tc ? nullptr : h->feats;
     p.feats16 = tc ? h->feats16 : nullptr;

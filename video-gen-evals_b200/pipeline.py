@@ -69,8 +69,10 @@ class TagScorer:
                           torch.from_numpy(seg).to(self.device), int(seg[-1]))
         return cache[key]
 
-    def encode(self, dv: DeviceVideos, want_frames: bool = False):
-        """-> dict(seq [N,256], tc_window [N], seg [V+1], frames [N,T+1,256]|None, flags int32[1])"""
+    def encode(self, dv: DeviceVideos, want_frames: bool = False, use_clips: Optional[bool] = None):
+        """-> dict(seq [N,256], tc_window [N], seg [V+1], frames [N,T+1,256]|None, flags int32[1]).
+        use_clips: None = tag_encode_clips whenever all videos have the same length (>= clip_len), False = always the
+        explicit window table (tag_encode_windows); both give the same windows in the same order."""
         lib = _lib.load()
         wv, ws, seg, N = self._table(dv)
         T = self.clip_len
@@ -80,10 +82,20 @@ class TagScorer:
         frames = torch.empty(N, T + 1, 256, device=self.device, dtype=torch.float32) if want_frames else None
         flags = torch.zeros(1, device=self.device, dtype=torch.int32)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        lens = dv.lengths
+        L = int(lens[0]) if len(lens) else 0
+        uniform = len(lens) > 0 and L >= T and all(int(x) == L for x in lens) and use_clips is not False
         with torch.cuda.device(self.device):
-            _lib.check(h, lib.tag_encode_windows(h, C.byref(dv.c), _lib.ptr(self.mean), _lib.ptr(self.std), wv.data_ptr(),
-                                                 ws.data_ptr(), N, T, seq.data_ptr(), _lib.ptr(frames), None, tcw.data_ptr(),
-                                                 flags.data_ptr(), stream), "tag_encode_windows")
+            if uniform:
+                # clips of equal length on the reference's regular window grid: the library can build the features once per
+                # source frame and let the stem GEMMs gather the (overlapping) windows
+                _lib.check(h, lib.tag_encode_clips(h, C.byref(dv.c), _lib.ptr(self.mean), _lib.ptr(self.std), len(lens), L, T,
+                                                   self.stride, seq.data_ptr(), _lib.ptr(frames), None, tcw.data_ptr(),
+                                                   flags.data_ptr(), stream), "tag_encode_clips")
+            else:
+                _lib.check(h, lib.tag_encode_windows(h, C.byref(dv.c), _lib.ptr(self.mean), _lib.ptr(self.std), wv.data_ptr(),
+                                                     ws.data_ptr(), N, T, seq.data_ptr(), _lib.ptr(frames), None, tcw.data_ptr(),
+                                                     flags.data_ptr(), stream), "tag_encode_windows")
         return {"seq": seq, "tc_window": tcw, "seg": seg, "frames": frames, "flags": flags, "win_video": wv}
 
     # ------------------------------------------------------------------ centroid build (config 3)
