@@ -21,11 +21,15 @@
 // 1.55-1.75 GHz under sw_power_cap), not by L2->SM bandwidth, and the deeper {A,B} ring hides latency better than
 // 2 A + 6 B stages. Kept selectable because it is the right design if the L2 path ever becomes the limiter.
 //
-// CTA = 320 threads, persistent over 128x256 output tiles:
-//   warp 0      TMA producer (one elected lane), 4-stage ring of {A 128x64, B 256x64} fp16 tiles
-//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma 128x256x16 per stage
-//   warps 2..9  epilogue: tcgen05.ld 32 lanes x 32 columns at a time; 2 TMEM accumulator buffers
-//               (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+// CTA = 576 threads (18 warps), one CTA per SM, persistent over output tiles; by default two CTAs form a cluster and one
+// cta_group::2 MMA (256x256 tile per pair, 128 rows per CTA):
+//   warp 0       TMA producer (one elected lane): ring of {A 128x64, B 128x64 (pair) / 256x64 (single)} fp16 tiles
+//   warp 1       TMEM allocator + MMA issuer (one elected lane of the leader CTA): 4 x tcgen05.mma M256 N256 K16 per stage
+//   warps 2..17  epilogue (4 per TMEM lane quarter x 4 column groups): tcgen05.ld 32 lanes x 16 columns at a time, math in
+//                registers, every global access staged through a swizzled per-warp shared-memory tile; 2 TMEM accumulator
+//                buffers (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1
+// MODE 1 fuses GroupNorm over whole (T x 256) windows, MODE 2 LayerNorm over the 256 output columns (see k_gemm_tc).
+// Mode 3 of the producer gathers the rows of each window from a per-frame table (GemmTC::g_*, frame-table mode).
 // Descriptor encodings follow the PTX ISA tcgen05 matrix/instruction descriptor tables (cross-checked
 // against CUTLASS cute/arch/mma_sm100_desc.hpp).
 #include <cuda.h>
