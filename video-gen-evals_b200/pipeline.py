@@ -120,8 +120,10 @@ class TagScorer:
         lib = _lib.load()
         enc = self.encode(dv)
         V = dv.n_videos
-        if labels is None:
-            labels = torch.tensor(dv.vb.cls_idx, device=self.device, dtype=torch.int32)
+        if labels is None:                                   # class index per video, cached on the batch object
+            labels = dv.__dict__.get("_labels")
+            if labels is None:
+                labels = dv.__dict__["_labels"] = torch.tensor(dv.vb.cls_idx, device=self.device, dtype=torch.int32)
         ac = torch.empty(V, device=self.device, dtype=torch.float32)
         tc = torch.empty(V, device=self.device, dtype=torch.float32)
         h = util_handle(self.device)
