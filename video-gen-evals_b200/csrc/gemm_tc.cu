@@ -79,6 +79,8 @@ struct TcParams {
   int64_t M;
   int N;
   int kb_per_tap;       // K / 64
+  int kseg;             // plain GEMM over two activation tensors, C = [A | A2] W^T (K2 == K): number of extra K segments (0 / 1),
+  int seg_flip;         //   reached through the third TMA coordinate; seg_flip: A2 lies below A in memory
   int taps, dil;
   int mode;             // 0 plain rows, 1 conv with T <= 128 (tile = 128/T windows), 2 conv with T % 128 == 0,
                         // 3 plain GEMM whose rows are gathered window by window from a per-frame table
@@ -397,7 +399,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int n_kb = p.taps * p.kb_per_tap;
+  const int n_kb = (p.taps + p.kseg) * p.kb_per_tap;
   // work items: (m-tile, n-tile) per CTA, or (pair of m-tiles, n-tile) per cluster
   const int64_t total_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const int64_t tile0 = PAIR ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
@@ -467,6 +469,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           const int j = kb / p.kb_per_tap;
           const int kc = kb - j * p.kb_per_tap;
           const int shift = (p.taps > 1) ? (j - p.taps / 2) * p.dil : 0;
+          const int c2k = c2 + (p.kseg ? (p.seg_flip ? 1 - j : j) : 0);      // second K segment = second slice of the 3-D map
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint32_t tx = (ld_a ? A_BYTES : 0) + (ld_b ? Cfg<PAIR>::B_BYTES : 0);
@@ -477,7 +480,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               for (int i = 0; i < 8; ++i)
                 if (i < p.wpt) tma_load_3d_pair(sa + (uint32_t)(i * p.T) * 128u, &map_a, full_bar(stage), kc * BLOCK_K, grow[i], 0);
             } else
-            if (ld_a) tma_load_3d_pair(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+            if (ld_a) tma_load_3d_pair(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2k);
             if (ld_b) tma_load_2d_pair(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
           } else {
             if (tx) mbar_arrive_expect_tx(full_bar(stage), tx); else mbar_arrive(full_bar(stage));
@@ -486,7 +489,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               for (int i = 0; i < 8; ++i)
                 if (i < p.wpt) tma_load_3d(sa + (uint32_t)(i * p.T) * 128u, &map_a, full_bar(stage), kc * BLOCK_K, grow[i], 0);
             } else
-            if (ld_a) tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2);
+            if (ld_a) tma_load_3d(sa, &map_a, full_bar(stage), kc * BLOCK_K, c1_base + shift, c2k);
             if (ld_b) tma_load_2d(sa + A_BYTES, &map_b, full_bar(stage), kb * BLOCK_K, n_tile * BLOCK_N);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -913,7 +916,9 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   if (g.K % BLOCK_K || g.K <= 0) return bad("K must be a positive multiple of 64");
   if (g.lda % 8 || (reinterpret_cast<uintptr_t>(g.A) & 15)) return bad("A must be 16-byte aligned with lda % 8 == 0");
   if (reinterpret_cast<uintptr_t>(g.W) & 15) return bad("W must be 16-byte aligned");
-  if (g.A2 != nullptr) return bad("second K segment not built yet");
+  if (g.A2 != nullptr && (g.taps != 1 || g.g_L > 0 || g.K2 != g.K || g.lda2 != g.lda || g.A2 == g.A ||
+                          ((reinterpret_cast<uintptr_t>(g.A2) - reinterpret_cast<uintptr_t>(g.A)) & 15)))
+    return bad("a second K segment needs a plain GEMM and a second activation tensor of the same shape and row pitch");
   const bool ln = g.ln_gamma != nullptr;
   if (ln) {
     if (g.ln_beta == nullptr || g.taps != 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 == nullptr || g.res32 == nullptr ||
@@ -1008,6 +1013,14 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     box[0] = BLOCK_K; box[1] = BLOCK_M; box[2] = 1;
     gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)g.M; gdim[2] = 1;
     gstr[0] = (cuuint64_t)g.lda * 2; gstr[1] = (cuuint64_t)g.M * g.lda * 2;
+    if (g.A2 != nullptr) {
+      // the two activation tensors become the two slices of one 3-D map (slice stride = their distance in memory)
+      const uintptr_t a = reinterpret_cast<uintptr_t>(g.A), a2 = reinterpret_cast<uintptr_t>(g.A2);
+      const uint64_t dist = a2 > a ? a2 - a : a - a2;
+      if (dist < (uint64_t)g.M * g.lda * 2 || dist >= (1ull << 40)) return bad("the two K-segment tensors overlap or are too far apart");
+      p.kseg = 1; p.seg_flip = a2 < a ? 1 : 0;
+      gdim[2] = 2; gstr[1] = dist;
+    }
   }
   if (g.row0_vec != nullptr) {
     if (g.C16 == nullptr || g.T < 1 || (g.T & (g.T - 1)) || g.gn_gamma != nullptr || ln || (reinterpret_cast<uintptr_t>(g.row0_vec) & 15))
@@ -1015,11 +1028,12 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     p.row0_vec = g.row0_vec;
   }
   CUtensorMap map_a, map_b;
-  CUresult r = ctx->encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(g.A), gdim, gstr, box, estr,
+  const __half* a_base = (g.A2 != nullptr && p.seg_flip) ? g.A2 : g.A;
+  CUresult r = ctx->encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(a_base), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(A) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
-  const int64_t ktot = (int64_t)g.taps * g.K;
+  const int64_t ktot = (int64_t)(g.taps + p.kseg) * g.K;
   cuuint64_t bdim[2] = {(cuuint64_t)ktot, (cuuint64_t)g.N};
   cuuint64_t bstr[1] = {(cuuint64_t)ktot * 2};
   cuuint32_t bbox[2] = {BLOCK_K, (cuuint32_t)(pair ? BLOCK_N / 2 : BLOCK_N)};

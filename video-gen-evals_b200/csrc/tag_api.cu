@@ -28,6 +28,7 @@ struct EncWeights {                 // one MovementConvEncoder (model.py:43-58)
   __half* stem16 = nullptr;         // [256, k16] (k16 = d_in rounded up to 64)
   __half* conv16[8][2] = {};
   __half* proj16 = nullptr;
+  __half* projcat16 = nullptr;      // state encoders only: [256, 512] = [proj_state | proj_motion] (one GEMM for s = state + motion)
 };
 
 struct LayerWeights {               // nn.TransformerEncoderLayer (model.py:145)
@@ -315,7 +316,7 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
                     float* tokens, float* tcw, const ClipGather* cg = nullptr) {
   const int64_t R = W * T, R2 = W * (T + 1);
   const int M = h->M;
-  __half* bufH = (__half*)h->bufH; __half* bufY1 = (__half*)h->bufY1; __half* bufY2 = (__half*)h->bufY2;
+  __half* bufY1 = (__half*)h->bufY1; __half* bufY2 = (__half*)h->bufY2;
   int rc;
   int e_idx = 0;
   MergeParams mp{};
@@ -323,8 +324,12 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
   const int kk = h->cfg.conv_kernel;
   for (int m = 0; m < M; ++m) {
     for (int side = 0; side < 2; ++side) {
-      if (side == 1 && h->cfg.diff_dims[m] <= 0) { mp.pm[m] = nullptr; continue; }
+      if (side == 1 && h->cfg.diff_dims[m] <= 0) continue;
       const EncWeights& e = side == 0 ? h->state[m] : h->motion[m];
+      const bool has_motion = h->cfg.diff_dims[m] > 0;
+      // the state encoder's final hidden state waits in its own buffer for the motion encoder's: s = state + motion
+      // (model.py:174) is ONE projection GEMM over K = [h_state | h_motion]
+      __half* bufH = (side == 0 && has_motion) ? (__half*)h->fusedB : (__half*)h->bufH;
       GemmTC g{};
       g.A = feats16 + (side == 0 ? h->raw_off16[m] : h->diff_off16[m]); g.M = R; g.lda = h->D16;
       g.W = e.stem16; g.N = kD; g.K = e.k16; g.taps = 1; g.dil = 1; g.T = T; g.C16 = bufH; g.ldc = kD;
@@ -352,12 +357,18 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
           { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_groupnorm<__half>(bufY2, e.gn_g[b], e.gn_b[b], bufH, W, T, s)); }
         }
       }
+      if (side == 0 && has_motion) continue;
       __half* P = (__half*)h->P[e_idx++];
       GemmTC pj{};
-      pj.A = bufH; pj.M = R; pj.lda = kD; pj.W = e.proj16; pj.N = kD; pj.K = kD; pj.taps = 1; pj.dil = 1; pj.T = T;
-      pj.C16 = P; pj.ldc = kD;
-      rc = gemm_tc_run(h, s, pj, 2.0 * R * kD * kD); if (rc) return rc;
-      if (side == 0) mp.ps[m] = P; else mp.pm[m] = P;
+      pj.M = R; pj.N = kD; pj.K = kD; pj.taps = 1; pj.dil = 1; pj.T = T; pj.C16 = P; pj.ldc = kD;
+      if (side == 1) {
+        pj.A = (const __half*)h->fusedB; pj.lda = kD; pj.A2 = bufH; pj.lda2 = kD; pj.K2 = kD; pj.W = h->state[m].projcat16;
+        rc = gemm_tc_run(h, s, pj, 2.0 * R * kD * 2 * kD); if (rc) return rc;
+      } else {
+        pj.A = bufH; pj.lda = kD; pj.W = e.proj16;
+        rc = gemm_tc_run(h, s, pj, 2.0 * R * kD * kD); if (rc) return rc;
+      }
+      mp.ps[m] = P; mp.pm[m] = nullptr;
     }
     mp.inv_tau[m] = h->inv_tau[m];
     mp.lbias[m] = h->lbias[m];
@@ -589,7 +600,18 @@ int tag_finalize_weights(tag_handle* h) {
   }
   for (int m = 0; m < h->M; ++m) {
     rc = pack_encoder(h, "state_enc." + std::to_string(m), h->cfg.raw_dims[m], &h->state[m]); if (rc) return rc;
-    if (h->cfg.diff_dims[m] > 0) { rc = pack_encoder(h, "motion_enc." + std::to_string(m), h->cfg.diff_dims[m], &h->motion[m]); if (rc) return rc; }
+    if (h->cfg.diff_dims[m] > 0) {
+      rc = pack_encoder(h, "motion_enc." + std::to_string(m), h->cfg.diff_dims[m], &h->motion[m]); if (rc) return rc;
+      if (h->cfg.precision == TAG_PRECISION_FP16_TC) {
+        const auto* ps = find_w(h, "state_enc." + std::to_string(m) + ".proj.weight", {kD, kD});
+        const auto* pm = find_w(h, "motion_enc." + std::to_string(m) + ".proj.weight", {kD, kD});
+        if (!ps || !pm) return TAG_ERR_MISSING;
+        std::vector<float> cat((size_t)kD * 2 * kD);
+        for (int n = 0; n < kD; ++n)
+          for (int k = 0; k < kD; ++k) { cat[(size_t)n * 2 * kD + k] = (*ps)[(size_t)n * kD + k]; cat[(size_t)n * 2 * kD + kD + k] = (*pm)[(size_t)n * kD + k]; }
+        rc = upload(h, &h->state[m].projcat16, to_half(cat)); if (rc) return rc;
+      }
+    }
   }
   // ---- fusion (model.py:61-98): the query is input independent, fold it into one 256-vector
   const auto* latent = find_w(h, "fusion.latent", {1, 1, kD});
