@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) k_merge_fusion(const MergeParams p) {
 // in total instead of three per modality), and kv is never materialised:
 //   logit_m = sc_m * sum_k d_m[k] g[k] qk[k] + sum_k b[k] qk[k],   mix[k] = g[k] * sum_m (a_m sc_m) d_m[k] + b[k]
 // with d_m = s_m - mean_m, sc_m = rstd1 * rstd2 (see above), a = softmax(logit) (sum_m a_m = 1).
-template <int MM>
+// HM = false: no separate motion tensors (the encoder already produced s = state + motion in one projection GEMM)
+template <int MM, bool HM>
 __global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
   const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
     us[m] = make_uint4(0u, 0u, 0u, 0u); um[m] = us[m];
     if (m < p.M) {
       us[m] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.ps[m]) + r * kD + lane * 8));
-      if (p.pm[m] != nullptr) um[m] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.pm[m]) + r * kD + lane * 8));
+      if (HM && p.pm[m] != nullptr) um[m] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.pm[m]) + r * kD + lane * 8));
     }
   }
   float g[8], b[8], gq[8];
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
     s1[m] = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 a = __half22float2(hs[i]), c = __half22float2(hm[i]);
+      const float2 a = __half22float2(hs[i]);
+      const float2 c = HM ? __half22float2(hm[i]) : make_float2(0.f, 0.f);
       d[m][2 * i] = a.x + c.x; d[m][2 * i + 1] = a.y + c.y;            // s = state + motion  (model.py:174)
       s1[m] += d[m][2 * i] + d[m][2 * i + 1];
     }
@@ -733,8 +735,10 @@ cudaError_t launch_merge_fusion(const MergeParams& p, cudaStream_t s) {
   if (p.R <= 0) return cudaSuccess;
   const unsigned grid = (unsigned)((p.R + 7) / 8);
   if constexpr (sizeof(TA) == 2) {
-    if (p.M <= 5) k_merge_fusion_h<5><<<grid, 256, 0, s>>>(p);
-    else k_merge_fusion_h<TAG_MAX_MODALITIES><<<grid, 256, 0, s>>>(p);
+    bool hm = false;
+    for (int m = 0; m < p.M; ++m) hm = hm || p.pm[m] != nullptr;
+    if (p.M <= 5) { if (hm) k_merge_fusion_h<5, true><<<grid, 256, 0, s>>>(p); else k_merge_fusion_h<5, false><<<grid, 256, 0, s>>>(p); }
+    else { if (hm) k_merge_fusion_h<TAG_MAX_MODALITIES, true><<<grid, 256, 0, s>>>(p); else k_merge_fusion_h<TAG_MAX_MODALITIES, false><<<grid, 256, 0, s>>>(p); }
     return cudaGetLastError();
   }
   k_merge_fusion<TA><<<grid, 256, 0, s>>>(p);
