@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
 #pragma unroll
   for (int m = 0; m < MM; ++m) {
     const float var = s2[m] * (1.0f / kD);
-    const float rstd1 = 1.0f / sqrtf(var + kLnEps);
+    const float rstd1 = rsqrtf(var + kLnEps);                 // MUFU.RSQ (2^-22 relative): far below the fp16 rounding of the result
     const float var_u = var * rstd1 * rstd1;                  // variance of the first LayerNorm's output
-    sc[m] = rstd1 / sqrtf(var_u + kLnEps);
+    sc[m] = rstd1 * rsqrtf(var_u + kLnEps);
     logit[m] = -CUDART_INF_F;
     if (m < p.M) {
       logit[m] = fmaf(sc[m], sq[m], bq) * p.inv_tau[m] + p.lbias[m];    // Q . (Wk kv) / sqrt(D), model.py:89-91
@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
   }
   float den = 0.f;
 #pragma unroll
-  for (int m = 0; m < MM; ++m) { logit[m] = (m < p.M) ? expf(logit[m] - mx) : 0.f; den += logit[m]; }
-  const float inv_den = 1.0f / den;
+  for (int m = 0; m < MM; ++m) { logit[m] = (m < p.M) ? __expf(logit[m] - mx) : 0.f; den += logit[m]; }
+  const float inv_den = __fdividef(1.0f, den);
   float mix[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) mix[k] = 0.f;
