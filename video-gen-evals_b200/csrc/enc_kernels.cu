@@ -378,6 +378,13 @@ __global__ void __launch_bounds__(640) k_attention(const TA* __restrict__ qkv, T
 constexpr int kAttS = 48, kQStride = 40;
 constexpr int kAttWarpHalfs = 3 * kAttS * kQStride;                      // Q + K + V per warp
 
+// 2^x on the MUFU (softmax arguments are <= 0 and scores far from the denormal range; -inf -> 0)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -453,22 +460,24 @@ __global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict_
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
 #pragma unroll
     for (int nt = 0; nt < 6; ++nt) {
-      const int c0 = nt * 8 + 2 * tig;
+      if (nt * 8 + 8 > S) {                              // only the tiles that contain padding keys need the mask
+        const int c0 = nt * 8 + 2 * tig;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = c0 + (e & 1);
-        sc[mt][nt][e] = (col < S) ? sc[mt][nt][e] * scale : -CUDART_INF_F;
+        for (int e = 0; e < 4; ++e)
+          if (c0 + (e & 1) >= S) sc[mt][nt][e] = -CUDART_INF_F;
       }
       mx0 = fmaxf(mx0, fmaxf(sc[mt][nt][0], sc[mt][nt][1]));
       mx1 = fmaxf(mx1, fmaxf(sc[mt][nt][2], sc[mt][nt][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 2));
+    // softmax(q.k / sqrt(32)): p = 2^(s * scale - max * scale) — scale > 0, so the raw maximum is the scaled one's argmax
+    const float m0s = -mx0 * scale, m1s = -mx1 * scale;
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 6; ++nt) {
-      sc[mt][nt][0] = exp2f(sc[mt][nt][0] - mx0); sc[mt][nt][1] = exp2f(sc[mt][nt][1] - mx0);
-      sc[mt][nt][2] = exp2f(sc[mt][nt][2] - mx1); sc[mt][nt][3] = exp2f(sc[mt][nt][3] - mx1);
+      sc[mt][nt][0] = ex2_fast(fmaf(sc[mt][nt][0], scale, m0s)); sc[mt][nt][1] = ex2_fast(fmaf(sc[mt][nt][1], scale, m0s));
+      sc[mt][nt][2] = ex2_fast(fmaf(sc[mt][nt][2], scale, m1s)); sc[mt][nt][3] = ex2_fast(fmaf(sc[mt][nt][3], scale, m1s));
       s0 += sc[mt][nt][0] + sc[mt][nt][1];
       s1 += sc[mt][nt][2] + sc[mt][nt][3];
     }
@@ -596,27 +605,31 @@ __global__ void __launch_bounds__(128) k_attention_flash(const __half* __restric
           mma_16816(sc[nt], aq[ks], bk);
         }
       }
-      float mx0 = m0, mx1 = m1;
+      float mx0 = m0, mx1 = m1;                           // running maxima of the RAW scores (scale > 0)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const int c0 = kc + nt * 8 + 2 * tig;
+        if (kc + nt * 8 + 8 > S) {                         // only tiles with padding keys need the mask
+          const int c0 = kc + nt * 8 + 2 * tig;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) sc[nt][e] = (c0 + (e & 1) < S) ? sc[nt][e] * scale : -CUDART_INF_F;
+          for (int e = 0; e < 4; ++e)
+            if (c0 + (e & 1) >= S) sc[nt][e] = -CUDART_INF_F;
+        }
         mx0 = fmaxf(mx0, fmaxf(sc[nt][0], sc[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(sc[nt][2], sc[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(FULL_MASK, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(FULL_MASK, mx1, 2));
       // every chunk holds at least one real key (S_pad - S < 32), so mx is finite from the first chunk on
-      const float a0 = exp2f(m0 - mx0), a1 = exp2f(m1 - mx1);
+      const float a0 = ex2_fast((m0 - mx0) * scale), a1 = ex2_fast((m1 - mx1) * scale);
       m0 = mx0; m1 = mx1;
+      const float m0s = -mx0 * scale, m1s = -mx1 * scale;
       l0 *= a0; l1 *= a1;
 #pragma unroll
       for (int nd = 0; nd < 4; ++nd) { o[nd][0] *= a0; o[nd][1] *= a0; o[nd][2] *= a1; o[nd][3] *= a1; }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        sc[nt][0] = exp2f(sc[nt][0] - mx0); sc[nt][1] = exp2f(sc[nt][1] - mx0);
-        sc[nt][2] = exp2f(sc[nt][2] - mx1); sc[nt][3] = exp2f(sc[nt][3] - mx1);
+        sc[nt][0] = ex2_fast(fmaf(sc[nt][0], scale, m0s)); sc[nt][1] = ex2_fast(fmaf(sc[nt][1], scale, m0s));
+        sc[nt][2] = ex2_fast(fmaf(sc[nt][2], scale, m1s)); sc[nt][3] = ex2_fast(fmaf(sc[nt][3], scale, m1s));
         l0 += sc[nt][0] + sc[nt][1];
         l1 += sc[nt][2] + sc[nt][3];
       }
