@@ -20,6 +20,6 @@ from .features import (ModalityStats, DeviceVideos, FeatureFuser, WindowDataset,
 from .scoring import (extract_window_features, compute_temporal_coherence_scores,
                       compute_action_consistency_scores, build_train_centroids_subset, centroid_accumulate,
                       centroid_finalize, allreduce_centroid_sums, TCL, write_video_scores)
-from .pipeline import TagScorer, shard_range, window_table
+from .pipeline import TagScorer, block_plan, shard_range, window_table
 
 __all__ = [n for n in dir() if not n.startswith("_")]

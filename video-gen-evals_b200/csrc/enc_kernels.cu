@@ -799,11 +799,14 @@ cudaError_t launch_attention(const TA* qkv, TA* out, int64_t n_windows, int S, i
     const int S_pad = (S + 31) / 32 * 32;
     const size_t smem = (size_t)3 * S_pad * kQStride * sizeof(__half);
     if (smem <= 200 * 1024 && n_windows * n_heads < (1ll << 31)) {
-      static size_t configured = 48 * 1024;
-      if (smem > configured) {
+      static size_t configured[64];                     // per device: function attributes are device state
+      int dev = 0;
+      cudaGetDevice(&dev);
+      size_t& cfg = configured[dev & 63];
+      if (smem > 48 * 1024 && smem > cfg) {
         cudaError_t e = cudaFuncSetAttribute(k_attention_flash, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        cfg = smem;
       }
       k_attention_flash<<<(unsigned)(n_windows * n_heads), 128, smem, s>>>(qkv, out, S, S_pad, n_heads);
       return cudaGetLastError();

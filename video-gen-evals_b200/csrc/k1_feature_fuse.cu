@@ -661,7 +661,10 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
       pl.bar_off = (pl.inv_off + TAG_MAX_MODALITIES * (kS + 1) * 4 + TAG_MAX_MODALITIES * 4 + 15) & ~15;
       const int smem_total = pl.bar_off + 16;
       if (smem_total <= 227 * 1024) {
-        static int configured = 0;
+        static int configured_dev[64];                    // per device: function attributes are device state
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int& configured = configured_dev[dev & 63];
         if (configured < smem_total) {
           cudaError_t e = cudaFuncSetAttribute(k_feature_fuse_staged<kS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
           if (e == cudaSuccess) e = cudaFuncSetAttribute(k_feature_fuse_staged<kS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);

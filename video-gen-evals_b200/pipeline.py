@@ -45,6 +45,26 @@ def window_table(lengths: Sequence[int], clip_len: int, stride: int):
     return win_video.astype(np.int32), win_start.astype(np.int32), seg
 
 
+def block_plan(lengths: Sequence[int], clip_len: int, stride: int, max_windows: int, first: bool,
+               n_sms: int = 148) -> List[Tuple[int, int]]:
+    """Cut a batch of videos into contiguous blocks `(lo, hi)` for `TagScorer.score_stream`: every block is at most one
+    encoder pass (<= max_windows windows; a video's windows never straddle two blocks), and the FIRST batch of a stream
+    starts with short blocks (1, 3, 15 waves of the CTA-pair GEMM) so that only a sliver of host->device copy is exposed
+    before the encoder has work. A wave = (n_sms // 2) tile pairs of 256 rows = (n_sms // 2) * 256 / clip_len windows."""
+    seg = window_table(lengths, clip_len, stride)[2]                           # cumulative windows per video
+    wave = max(1, (n_sms // 2) * 256 // max(1, clip_len))
+    cap = max(1, int(max_windows))
+    steps = [wave, 3 * wave, 15 * wave] if first else []
+    blocks, lo, V = [], 0, len(lengths)
+    while lo < V:
+        want = min(steps.pop(0), cap) if steps else cap
+        hi = int(np.searchsorted(seg, seg[lo] + want, side="right")) - 1       # last video that still fits
+        hi = max(hi, lo + 1)
+        blocks.append((lo, min(hi, V)))
+        lo = min(hi, V)
+    return blocks
+
+
 class TagScorer:
     def __init__(self, model: HumanActionScorer, stats, clip_len: int = 32, stride: int = 8, device=None):
         self.model = model
@@ -136,23 +156,8 @@ class TagScorer:
         return ac, tc
 
     def _block_plan(self, lengths: Sequence[int], first: bool) -> List[Tuple[int, int]]:
-        """Cut a batch into contiguous blocks of videos for `score_stream` (pieces=None): every block is one encoder
-        pass (<= model.max_windows windows), and the FIRST batch of a stream starts with short blocks (1, 3, 15 GEMM
-        waves) so that only a sliver of host->device copy is exposed before the encoder has work."""
-        seg = window_table(lengths, self.clip_len, self.stride)[2]             # cumulative windows per video
-        T = self.clip_len
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        wave = max(1, (sms // 2) * 256 // T)                                   # windows per wave of the CTA-pair GEMM
-        cap = max(1, int(self.model.max_windows))
-        steps = [wave, 3 * wave, 15 * wave] if first else []
-        blocks, lo, V = [], 0, len(lengths)
-        while lo < V:
-            want = min(steps.pop(0), cap) if steps else cap
-            hi = int(np.searchsorted(seg, seg[lo] + want, side="right")) - 1   # last video that still fits
-            hi = max(hi, lo + 1)
-            blocks.append((lo, min(hi, V)))
-            lo = min(hi, V)
-        return blocks
+        return block_plan(lengths, self.clip_len, self.stride, int(self.model.max_windows), first, sms)
 
     def score_stream(self, batches, centroids: torch.Tensor, pieces: Optional[int] = None, prefetch: int = 3):
         """Streaming end-to-end call: `batches` is an iterable of HOST (ideally pinned) VideoBatch objects; yields
