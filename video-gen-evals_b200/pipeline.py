@@ -104,7 +104,9 @@ class TagScorer:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         lens = dv.lengths
         L = int(lens[0]) if len(lens) else 0
-        uniform = len(lens) > 0 and L >= T and all(int(x) == L for x in lens) and use_clips is not False
+        if "_uniform_len" not in dv.__dict__:                # cached on the batch object
+            dv.__dict__["_uniform_len"] = len(lens) > 0 and all(int(x) == L for x in lens)
+        uniform = dv.__dict__["_uniform_len"] and L >= T and use_clips is not False
         with torch.cuda.device(self.device):
             if uniform:
                 # clips of equal length on the reference's regular window grid: the library can build the features once per
