@@ -111,7 +111,8 @@ def test_gemm_tc_rejects_unsupported_shapes():
     assert lib.tag_debug_gemm_tc(h, A.data_ptr(), 256, W.data_ptr(), 96, 256, 256, 1, 1, 1, None, None, None, Cc.data_ptr(), None, 1, g.data_ptr(), g.data_ptr(), None, None, s) != 0
 
 
-@pytest.mark.parametrize("W_,T,dil", [(8, 32, 1), (37, 32, 8), (12, 16, 2), (5, 64, 4), (3, 128, 8), (150 * 4, 32, 2), (9, 8, 1)])
+@pytest.mark.parametrize("W_,T,dil", [(8, 32, 1), (37, 32, 8), (12, 16, 2), (5, 64, 4), (3, 128, 8), (150 * 4, 32, 2), (9, 8, 1),
+                                      (1, 256, 8), (7, 256, 2), (160, 256, 4)])   # T = 256: statistics cross the CTA pair
 def test_gemm_tc_fused_groupnorm(W_, T, dil):
     """conv2 form of reference TemporalConvBlock (model.py:38-40): GroupNorm(1,256)(GELU(conv(y) + res)) in one kernel,
     written in place over the residual buffer as the encoder does."""

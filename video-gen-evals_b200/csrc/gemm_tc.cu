@@ -79,6 +79,7 @@ struct TcParams {
   int64_t M;
   int N;
   int kb_per_tap;       // K / 64
+  int gn_xchg;          // fused GroupNorm with T == 256: a window spans both CTAs of the pair, statistics cross over DSMEM
   int kseg;             // plain GEMM over two activation tensors, C = [A | A2] W^T (K2 == K): number of extra K segments (0 / 1),
   int seg_flip;         //   reached through the third TMA coordinate; seg_flip: A2 lies below A in memory
   int taps, dil;
@@ -190,6 +191,37 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
 }
+// ---- CTA-pair exchange of GroupNorm statistics (T == 256: one window = the pair's two 128-row tiles)
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t smem_addr_cta, uint32_t peer_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr_cta), "r"(peer_rank));
+  return r;
+}
+__device__ __forceinline__ void st_peer_v2(uint32_t addr_cluster, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr_cluster), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer_release(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("gemm_tc: GroupNorm exchange wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -367,6 +399,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 4 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 6 + a); };
   const uint32_t tmem_slot = bar_base + 8u * MAX_BARS;
+  // GroupNorm pair exchange (T == 256): two mbarriers and two (sum, sumsq) slots, alternating by tile parity
+  auto xbar = [&](int i) { return bar_base + 208u + 8u * i; };
+  auto xslot = [&](int i) { return bar_base + 224u + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s_gb = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + GN_RED_BYTES);
@@ -381,6 +416,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * (PAIR ? 2 : 1)); }
+    for (int a = 0; a < 2; ++a) mbar_init(xbar(a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (this kernel runs one CTA per SM)
@@ -631,7 +667,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             s1 += __shfl_xor_sync(FULL_MASK, s1, o);
             s2 += __shfl_xor_sync(FULL_MASK, s2, o);
           }
-          const int G = p.T > 32 ? p.T / 32 : 1;
+          const int Tl = p.T < BLOCK_M ? p.T : BLOCK_M;       // rows of the window inside this CTA's tile
+          const int G = Tl > 32 ? Tl / 32 : 1;
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
           asm volatile("bar.sync %0, %1;" ::"r"(1 + q / G), "r"(4 * G * 32) : "memory");
           for (int qq = 0; qq < G; ++qq) {
@@ -642,6 +679,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red + (uint32_t)((e * 32 + lane) * 8)) : "memory");
               S1 += a; S2 += b;
             }
+          }
+        }
+        if constexpr (PAIR) {
+          if (p.gn_xchg) {
+            // the window's other 128 rows live in the peer CTA: swap the per-CTA sums through the peer's shared memory.
+            // Barrier and slot alternate by tile parity: the peer can be at most one tile ahead (it needs this CTA's sums
+            // of tile i+1 to finish tile i+1), so an (i & 1) slot is never overwritten before it has been read.
+            const int xi = (int)(it & 1);
+            if (warp == 2 && lane == 0) {
+              st_peer_v2(map_to_peer(xslot(xi), rank ^ 1u), S1, S2);
+              mbar_arrive_peer_release(map_to_peer(xbar(xi), rank ^ 1u));
+            }
+            mbar_wait_cluster(xbar(xi), (uint32_t)((it >> 1) & 1));
+            float a, b;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(xslot(xi)) : "memory");
+            S1 += a; S2 += b;
           }
         }
         const float inv_n = 1.0f / ((float)p.T * (float)BLOCK_N);
@@ -904,6 +957,7 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
 }
 
 void tc_context_destroy(TcContext* c) { delete c; }
+bool tc_pair_enabled(const TcContext* c) { return c != nullptr && c->pair; }
 
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char* err, int errlen) {
   if (g.M <= 0) return cudaSuccess;
@@ -943,9 +997,11 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   p.dbg = ctx->dbg;
   const bool gn = g.gn_gamma != nullptr;
   if (gn) {
-    if (g.gn_beta == nullptr || g.taps <= 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 != nullptr || g.T > BLOCK_M ||
-        (g.T & (g.T - 1)) != 0)
-      return bad("fused GroupNorm needs a conv with N == 256, fp16 output and T a power of two <= 128");
+    const bool pair_ok = ctx->pair && (g.M + BLOCK_M - 1) / BLOCK_M >= 2;
+    if (g.gn_beta == nullptr || g.taps <= 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 != nullptr ||
+        (g.T & (g.T - 1)) != 0 || (g.T > BLOCK_M && !(g.T == 2 * BLOCK_M && pair_ok)))
+      return bad("fused GroupNorm needs a conv with N == 256, fp16 output and T a power of two <= 128 (256 with CTA pairs)");
+    if (g.T == 2 * BLOCK_M) p.gn_xchg = 1;
   }
   p.n_tiles = g.N / BLOCK_N;
   p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
@@ -954,7 +1010,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   cuuint32_t box[3], estr[3] = {1, 1, 1};
   const bool pair = ctx->pair && p.m_tiles >= 2;
   const int b_bytes = (pair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
-  if (g.taps > 1 && ctx->halo != 0 && (g.taps & 1)) {
+  if (g.taps > 1 && ctx->halo != 0 && (g.taps & 1) && !p.gn_xchg) {
     // halo tiles: (t, window)-ordered rows, one load per 64-channel chunk (see the header comment)
     if (g.T >= 1 && g.M % g.T == 0 && ((g.T <= BLOCK_M && BLOCK_M % g.T == 0) || g.T % BLOCK_M == 0)) {
       const int tp = g.T <= BLOCK_M ? g.T : BLOCK_M;              // frames of a tile

@@ -126,4 +126,5 @@ struct GemmTC {
 struct TcContext;   // opaque: driver entry points + cached tensor maps
 TcContext* tc_context_create(int device, char* err, int errlen);
 void tc_context_destroy(TcContext*);
+bool tc_pair_enabled(const TcContext*);   // CTA pairs (cta_group::2) in use: fused GroupNorm then also covers T == 256
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char* err, int errlen);

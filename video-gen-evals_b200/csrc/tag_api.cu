@@ -345,7 +345,8 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
         rc = gemm_tc_run(h, s, c1, 2.0 * R * kD * kD * kk); if (rc) return rc;
         GemmTC c2 = c1;
         c2.A = bufY1; c2.W = e.conv16[b][1]; c2.res16 = bufH; c2.ldr = kD;
-        const bool fuse_gn = T <= 128 && (T & (T - 1)) == 0;
+        // a tile (T <= 128) or a CTA pair (T == 256) owns whole windows: GroupNorm fuses into conv2's epilogue
+        const bool fuse_gn = (T & (T - 1)) == 0 && (T <= 128 || (T == 256 && tc_pair_enabled(h->tc)));
         if (fuse_gn) {
           // conv2 + residual + GELU + GroupNorm in one kernel; in place over the residual (a thread reads and
           // later overwrites only its own row/column block)
