@@ -148,3 +148,24 @@ def test_oracle_fp64_noise_floor():
     wins = g.gen_windows()[:8]
     _, seq32, _, _ = _oracle_features(g, wins, g.gen)
     assert max_abs(seq32, g.npz["seq_embeds_fp64"][:8]) < 5e-6
+
+
+def test_window_rows_are_whole_clip_rows_except_the_first_frame():
+    """The invariant the frame-table mode of the CUDA path (tag_encode_clips) rests on, checked on the pinned oracle: the
+    z-scored feature row of frame t >= 1 of a window starting at s equals row s + t of the features computed over the
+    whole clip (utils.py:142-217 deltas depend only on the previous frame), while the window's first row has zero
+    differences whatever precedes it."""
+    g = golden_case("m5_t32")
+    stats = g.stats()
+    v = next(i for i in range(g.gen.n_videos) if g.gen.length(i) >= 64)
+    vid = g.gen.video(v)
+    L = g.gen.length(v)
+    whole, _ = O.window_features(vid, 0, L, stats, g.mods)
+    D_raw = sum(int(g.dims_raw[m]) for m in g.mods)
+    for s in (0, 8, 24, L - 32):
+        win, _ = O.window_features(vid, s, 32, stats, g.mods)
+        assert torch.equal(win[1:], whole[s + 1:s + 32])                       # bit-identical rows
+        assert torch.equal(win[0, :D_raw], whole[s, :D_raw])                   # raw part of the first row too
+        assert torch.equal(win[0, D_raw:], whole[0, D_raw:])                   # differences: the same z-scored zero everywhere
+        if s > 0:
+            assert not torch.equal(win[0, D_raw:], whole[s, D_raw:])           # ... not the clip's own difference at that frame
