@@ -31,3 +31,17 @@ for pieces, prefetch in ((2, 2), (2, 3), (None, 3), (None, 2), (4, 3)):
         pass
     torch.cuda.synchronize()
     print("pieces=%s prefetch=%d: %.2f ms/step" % (pieces, prefetch, (time.perf_counter() - t0) / 5 * 1e3), flush=True)
+
+# how much does a concurrent (independent) pinned H2D stream slow the HBM-resident step? (DMA + HBM-write contention / power)
+src = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+dst = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+cs = torch.cuda.Stream(device=dev)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    with torch.cuda.stream(cs):
+        for _ in range(2):                      # ~2 GB per step, like the end-to-end leg
+            dst.copy_(src, non_blocking=True)
+    scorer.score(dv, cen)
+torch.cuda.synchronize()
+print("resident + independent 2 GB/step H2D on a side stream: %.2f ms/step" % ((time.perf_counter() - t0) / 5 * 1e3))
