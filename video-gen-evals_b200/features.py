@@ -79,7 +79,9 @@ def stats_vectors(stats, modalities: Sequence[str], device) -> Tuple[Optional[to
 class DeviceVideos:
     """Packed per-frame arrays of V videos resident on one GPU + the `tag_videos` view of them."""
 
-    def __init__(self, vb: VideoBatch, modalities: Sequence[str], device):
+    def __init__(self, vb: VideoBatch, modalities: Sequence[str], device, frame_offset: Optional[torch.Tensor] = None):
+        """frame_offset: optional device int64 [V+1] tensor prepared by the caller (the streaming path stages it on its
+        copy stream, so that no host->device copy is ever queued on the compute stream)."""
         self.device = torch.device(device)
         self.modalities = list(modalities)
         self.vb = vb if vb.pose.device == self.device else vb.to(self.device)
@@ -92,8 +94,17 @@ class DeviceVideos:
             if t is None:
                 raise ValueError(f"modality '{m}' requested but the video batch has no such array")
             self.src.append(t.to(torch.float32).contiguous())
-        self.frame_offset = torch.tensor(self.vb.offsets, dtype=torch.int64, device=self.device)
         self.lengths = [self.vb.offsets[i + 1] - self.vb.offsets[i] for i in range(self.vb.n_videos)]
+        V = self.vb.n_videos
+        L0 = self.lengths[0] if V else 0
+        self.uniform_len = L0 if V and all(x == L0 for x in self.lengths) else None
+        if frame_offset is not None:
+            self.frame_offset = frame_offset
+        elif self.uniform_len is not None and self.device.type == "cuda" and self.vb.offsets[0] == 0:
+            # clips of one length: the offsets are an arithmetic progression — generated on the device, no host copy
+            self.frame_offset = torch.arange(V + 1, device=self.device, dtype=torch.int64) * int(L0)
+        else:
+            self.frame_offset = torch.tensor(self.vb.offsets, dtype=torch.int64, device=self.device)
         self.c = _lib.tag_videos()
         for i, t in enumerate(self.src):
             self.c.src[i] = t.data_ptr()

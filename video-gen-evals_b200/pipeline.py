@@ -83,6 +83,13 @@ class TagScorer:
         """window table of a video batch, cached ON the batch object (never keyed by id(): ids are reused)."""
         key = (self.clip_len, self.stride)
         cache = dv.__dict__.setdefault("_window_tables", {})
+        if key not in cache and dv.uniform_len is not None and dv.uniform_len >= self.clip_len and self.device.type == "cuda":
+            # clips of one length on the regular grid: the table is arithmetic — built on the device, no host copies
+            V, L, T, st = dv.n_videos, int(dv.uniform_len), self.clip_len, max(1, self.stride)
+            wpv = (L - T) // st + 1
+            idx = torch.arange(V * wpv, device=self.device, dtype=torch.int32)
+            cache[key] = (torch.div(idx, wpv, rounding_mode="floor").to(torch.int32), (idx % wpv) * st,
+                          torch.arange(V + 1, device=self.device, dtype=torch.int64) * wpv, V * wpv)
         if key not in cache:
             wv, ws, seg = window_table(dv.lengths, self.clip_len, self.stride)
             cache[key] = (torch.from_numpy(wv).to(self.device), torch.from_numpy(ws).to(self.device),
@@ -104,9 +111,7 @@ class TagScorer:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         lens = dv.lengths
         L = int(lens[0]) if len(lens) else 0
-        if "_uniform_len" not in dv.__dict__:                # cached on the batch object
-            dv.__dict__["_uniform_len"] = len(lens) > 0 and all(int(x) == L for x in lens)
-        uniform = dv.__dict__["_uniform_len"] and L >= T and use_clips is not False
+        uniform = dv.uniform_len is not None and L >= T and use_clips is not False
         with torch.cuda.device(self.device):
             if uniform:
                 # clips of equal length on the reference's regular window grid: the library can build the features once per
@@ -204,10 +209,19 @@ class TagScorer:
             if j - prefetch - 2 >= 0:
                 cs.wait_event(done[j - prefetch - 2])         # bound the device copies that are alive
             with torch.cuda.stream(cs):
-                piece = self._stage_block(vb.slice(lo, hi), j % ring_slots, cap)
+                # everything the block needs from the host goes over the COPY stream: a host->device copy queued on the
+                # compute stream would sit behind the prefetched blocks in the copy engine's queue and stall the encoder
+                hb = vb.slice(lo, hi)
+                piece = self._stage_block(hb, j % ring_slots, cap)
+                meta = vb.__dict__.get("_stream_meta")
+                if meta is None:                              # pinned once per host batch: class index and frame offsets
+                    meta = vb.__dict__["_stream_meta"] = (torch.tensor(vb.cls_idx, dtype=torch.int32).pin_memory(),
+                                                          torch.tensor(vb.offsets, dtype=torch.int64).pin_memory())
+                labels = meta[0][lo:hi].to(dev, non_blocking=True)
+                offs = meta[1][lo:hi + 1].to(dev, non_blocking=True) - int(vb.offsets[lo])
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            staged.append((vb, lo, hi, last, piece, ev))
+            staged.append((vb, lo, hi, last, (piece, labels, offs), ev))
 
         def finish(p):
             ev, host, flags = p
@@ -224,7 +238,10 @@ class TagScorer:
             if lo == 0:
                 out = torch.empty(2, vb.n_videos, device=dev, dtype=torch.float32)
                 flags = None
-            a, t_ = self.score(DeviceVideos(piece, self.model.modalities, dev), centroids)
+            piece, labels, offs = piece
+            labels.record_stream(main)                        # allocated on the copy stream, read by kernels of this one
+            offs.record_stream(main)
+            a, t_ = self.score(DeviceVideos(piece, self.model.modalities, dev, frame_offset=offs), centroids, labels=labels)
             out[0, lo:hi].copy_(a)
             out[1, lo:hi].copy_(t_)
             flags = self.last_flags if flags is None else flags + self.last_flags
