@@ -219,9 +219,15 @@ class TagScorer:
                                                           torch.tensor(vb.offsets, dtype=torch.int64).pin_memory())
                 labels = meta[0][lo:hi].to(dev, non_blocking=True)
                 offs = meta[1][lo:hi + 1].to(dev, non_blocking=True) - int(vb.offsets[lo])
+                lens = [hb.length(v) for v in range(hb.n_videos)]
+                table = None
+                if not (all(x == lens[0] for x in lens) and lens[0] >= self.clip_len):
+                    # ragged block: its explicit window table travels with it (equal-length blocks build theirs on the device)
+                    wv, ws, seg = window_table(lens, self.clip_len, self.stride)
+                    table = tuple(torch.from_numpy(x).pin_memory().to(dev, non_blocking=True) for x in (wv, ws, seg)) + (int(seg[-1]),)
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            staged.append((vb, lo, hi, last, (piece, labels, offs), ev))
+            staged.append((vb, lo, hi, last, (piece, labels, offs, table), ev))
 
         def finish(p):
             ev, host, flags = p
@@ -238,10 +244,13 @@ class TagScorer:
             if lo == 0:
                 out = torch.empty(2, vb.n_videos, device=dev, dtype=torch.float32)
                 flags = None
-            piece, labels, offs = piece
-            labels.record_stream(main)                        # allocated on the copy stream, read by kernels of this one
-            offs.record_stream(main)
-            a, t_ = self.score(DeviceVideos(piece, self.model.modalities, dev, frame_offset=offs), centroids, labels=labels)
+            piece, labels, offs, table = piece
+            dv = DeviceVideos(piece, self.model.modalities, dev, frame_offset=offs)
+            for t in (labels, offs) + (table[:3] if table is not None else ()):
+                t.record_stream(main)                         # allocated on the copy stream, read by kernels of this one
+            if table is not None:
+                dv.__dict__.setdefault("_window_tables", {})[(self.clip_len, self.stride)] = table
+            a, t_ = self.score(dv, centroids, labels=labels)
             out[0, lo:hi].copy_(a)
             out[1, lo:hi].copy_(t_)
             flags = self.last_flags if flags is None else flags + self.last_flags
