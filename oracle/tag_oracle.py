@@ -70,8 +70,8 @@ def rotmat_delta(R: torch.Tensor) -> torch.Tensor:
 
 def procrustes_kp_delta(kp: torch.Tensor, eps: float = 1e-6) -> Tuple[torch.Tensor, int]:
     """utils.py:177-217 including its `R = Vh @ U.T` (sic, :209) and the det<0 fix-up (:210-212).
-    Returns (delta [T,2K], number of frames with det(H) < 0). The det(H)<0 branch depends on
-    LAPACK's sign choice and is not closed-form reproducible."""
+    Returns (delta [T,2K], number of frames with det(H) < 0 — the mirror regime, whose result is pinned by
+    LAPACK's always-improper U; see procrustes_kp_delta_closed_form)."""
     T, D = kp.shape
     K = D // 2
     pts = kp.view(T, K, 2)
@@ -96,10 +96,13 @@ def procrustes_kp_delta(kp: torch.Tensor, eps: float = 1e-6) -> Tuple[torch.Tens
 
 
 def procrustes_kp_delta_closed_form(kp: torch.Tensor, eps: float = 1e-6) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Closed form of the above for det(H) > 0 (SURVEY.md §8a A6 parity note): with MKL/LAPACK's
-    2x2 SVD, Vh@U.T equals the transpose of the polar rotation of H, i.e. R = [[c, s], [-s, c]]
-    with angle = atan2(H10 - H01, H00 + H11). This is what the CUDA kernel evaluates; kept here
-    so the CPU suite can check the algebra against the SVD form. Returns (delta, detH[T])."""
+    """Closed form of the above (SURVEY.md §8a A6 parity note), what the CUDA kernel evaluates; kept here so
+    the CPU suite can check the algebra against the SVD form. LAPACK's 2x2 SVD (MKL, this image) always returns
+    an IMPROPER U (a reflection, det U = -1: measured on 60 k random H in both regimes), which pins `Vh @ U.T`
+    plus the det fix-up (utils.py:209-212) to R = [[c, s], [-s, c]] with
+        angle = atan2(H10 - H01, H00 + H11)   for det(H) >= 0  (transpose of the polar rotation of H)
+        angle = atan2(H10 + H01, H00 - H11)   for det(H) <  0  (angle of the polar reflection of H).
+    Returns (delta, detH[T])."""
     T, D = kp.shape
     K = D // 2
     pts = kp.view(T, K, 2)
@@ -109,14 +112,16 @@ def procrustes_kp_delta_closed_form(kp: torch.Tensor, eps: float = 1e-6) -> Tupl
     X = torch.cat([P[:1], P[:-1]], dim=0)
     Y = P
     H = torch.einsum("tka,tkb->tab", X, Y)
-    ang = torch.atan2(H[:, 1, 0] - H[:, 0, 1], H[:, 0, 0] + H[:, 1, 1])
+    det = H[:, 0, 0] * H[:, 1, 1] - H[:, 0, 1] * H[:, 1, 0]
+    mirror = det < 0
+    ang = torch.where(mirror, torch.atan2(H[:, 1, 0] + H[:, 0, 1], H[:, 0, 0] - H[:, 1, 1]),
+                      torch.atan2(H[:, 1, 0] - H[:, 0, 1], H[:, 0, 0] + H[:, 1, 1]))
     c, sn = torch.cos(ang), torch.sin(ang)
     # X @ R with R = [[c, s], [-s, c]]
     xr0 = X[..., 0] * c[:, None] - X[..., 1] * sn[:, None]
     xr1 = X[..., 0] * sn[:, None] + X[..., 1] * c[:, None]
     d = torch.stack([Y[..., 0] - xr0, Y[..., 1] - xr1], dim=-1)
     d[0] = 0.0
-    det = H[:, 0, 0] * H[:, 1, 1] - H[:, 0, 1] * H[:, 1, 0]
     det[0] = 1.0
     return d.reshape(T, D), det
 

@@ -228,10 +228,33 @@ def delta_fn_case():
     print("[deltas] done")
 
 
+def mirror_case():
+    """`_procrustes_kp_delta` (utils.py:177-217) in its det(H) < 0 regime (mirror-like consecutive frames): i.i.d. random
+    frames (about half of the pairs) and a smooth sequence whose odd frames are left/right flipped (every pair).
+    Separate file (deltas_mirror.npz) so that deltas.npz stays bit-identical to its first generation."""
+    g = np.random.default_rng(11)
+    out = {}
+    kp = torch.from_numpy(g.random((48, 120)).astype(np.float32))
+    out["iid.kp"] = kp.numpy()
+    out["iid.kp_delta"] = ref_utils._procrustes_kp_delta(kp).numpy()
+    kp = synth.make_videos(1, 40, seed=78).video(0)["keypoints"].clone()
+    flip = kp.view(40, 60, 2).clone()
+    flip[1::2, :, 0] = 1.0 - flip[1::2, :, 0]
+    kp = flip.reshape(40, 120)
+    out["flip.kp"] = kp.numpy()
+    out["flip.kp_delta"] = ref_utils._procrustes_kp_delta(kp).numpy()
+    np.savez_compressed(os.path.join(HERE, "deltas_mirror.npz"), **out)
+    print("[deltas_mirror] done")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "mirror":
+        mirror_case()
+        sys.exit(0)
     delta_fn_case()
+    mirror_case()
     # M=5, reference defaults clip_len 32 / stride 8 (eval.py:358-359); lengths cover: exact multiple,
     # ragged tail, == clip_len, short (padded) and clip_len+1
     run_case("m5_t32", appearance=False, real_n=20, real_len=48,

@@ -137,27 +137,93 @@ def test_feature_fuse_fp16_operand_matches_fp32_features(tag, with_stats):
     assert float(err.median()) < 2e-4
 
 
-def test_feature_fuse_reflection_flag():
-    """i.i.d. random keypoint frames land in the det(H) < 0 regime about half of the time; the kernel must
-    count them (known divergence) and agree with the oracle's count."""
+def _kp_videos(kp: torch.Tensor):
+    """a one-video batch whose keypoints are `kp` [L,120] (the other modalities are seeded filler)"""
+    vb = synth.make_videos(1, kp.shape[0], seed=5)
+    vb.kp = kp.clone()
+    return vb
+
+
+def test_feature_fuse_mirror_regime_matches_reference():
+    """det(H) < 0 (mirror-like consecutive keypoint frames, utils.py:202-215): K1 evaluates the polar-reflection closed
+    form and must reproduce the REFERENCE's own `_procrustes_kp_delta` output (tests/golden/deltas_mirror.npz: i.i.d.
+    random frames, and a smooth sequence whose odd frames are left/right flipped); such frames are still counted."""
     g = golden_case("m5_t32")
-    vb = synth.make_videos(2, 40, seed=5)
-    gen = torch.Generator().manual_seed(3)
-    vb.kp = torch.rand(vb.kp.shape, generator=gen)
-    dv, fuser = _dv_and_fuser(g, vb)
-    wv = torch.tensor([0, 1], dtype=torch.int32, device=DEV)
-    ws = torch.tensor([0, 4], dtype=torch.int32, device=DEV)
-    feats, flags = fuser.fuse(dv, wv, ws, 32, None, None)
-    n_ref = sum(O.window_features(vb.video(v), s, 32, None, g.mods)[1] for v, s in ((0, 0), (1, 4)))
-    assert n_ref > 5
-    assert int(flags.item()) == n_ref
-    # frames NOT in the reflection regime still match the SVD form
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deltas_mirror.npz"))
     off = sum(g.dims_raw.values()) + g.dims_diff["vit"] + g.dims_diff["global"] + g.dims_diff["pose"] + g.dims_diff["beta"]
-    for i, (v, s) in enumerate(((0, 0), (1, 4))):
-        ref, _ = O.window_features(vb.video(v), s, 32, None, g.mods)
-        _, det = O.procrustes_kp_delta_closed_form(vb.video(v)["keypoints"][s:s + 32])
-        ok = det > 0
-        assert max_abs(feats[i].cpu()[ok, off:off + 120], ref[ok, off:off + 120]) < 2e-6
+    for tag in ("iid", "flip"):
+        kp = torch.from_numpy(gold[f"{tag}.kp"])
+        L = kp.shape[0]
+        vb = _kp_videos(kp)
+        dv, fuser = _dv_and_fuser(g, vb)
+        wv = torch.zeros(1, dtype=torch.int32, device=DEV)
+        ws = torch.zeros(1, dtype=torch.int32, device=DEV)
+        feats, flags = fuser.fuse(dv, wv, ws, L, None, None)
+        _, det = O.procrustes_kp_delta_closed_form(kp)
+        n_mirror = int((det < 0).sum())
+        assert n_mirror >= (L - 1 if tag == "flip" else 10)
+        assert int(flags.item()) == n_mirror
+        assert max_abs(feats[0].cpu()[:, off:off + 120], gold[f"{tag}.kp_delta"]) < 2e-6, tag
+        # the staged (tensor-core path) K1 takes the same branch
+        lib = _lib.load()
+        d16 = C.c_int32(0)
+        _lib.check(fuser.handle, lib.tag_debug_feature_fuse16(fuser.handle, C.byref(dv.c), None, None, None, None, 0, L, None,
+                                                              C.byref(d16), None, None), "d16")
+        f16 = torch.full((L, d16.value), float("nan"), device=DEV, dtype=torch.float16)
+        fl16 = torch.zeros(1, device=DEV, dtype=torch.int32)
+        _lib.check(fuser.handle, lib.tag_debug_feature_fuse16(fuser.handle, C.byref(dv.c), None, None, wv.data_ptr(), ws.data_ptr(),
+                                                              1, L, f16.data_ptr(), C.byref(d16), fl16.data_ptr(),
+                                                              torch.cuda.current_stream().cuda_stream), "tag_debug_feature_fuse16")
+        torch.cuda.synchronize()
+        off16 = sum((int(g.dims_raw[m]) + 63) // 64 * 64 for m in g.mods) + \
+            sum((int(g.dims_diff[m]) + 63) // 64 * 64 for m in g.mods if m != "kp2d")
+        got = f16[:, off16:off16 + 120].float().cpu()
+        ref = torch.from_numpy(gold[f"{tag}.kp_delta"])
+        assert int(fl16.item()) == n_mirror
+        assert bool(((got - ref).abs() <= ref.abs() * 2.0 ** -10 + 1e-5).all()), tag
+
+
+def test_feature_fuse_delta_edge_vectors():
+    """The reference-made edge vectors of tests/golden/deltas.npz THROUGH K1 (not only the CPU oracle): rotations with
+    theta near pi and a duplicated frame (utils.py:130-140, :165-174), an all-zero appearance row (1e-12 clamp,
+    :142-147), invisible (-1) keypoints with a duplicated frame (:177-217)."""
+    g = golden_case("m5_t32")
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deltas.npz"))
+    raw_total = sum(g.dims_raw.values())
+    doff = {}
+    o = raw_total
+    for m in g.mods:
+        doff[m] = o
+        o += g.dims_diff[m]
+    # rotations: 16 frames x 4 joints of edge.R fill joints 0..3 of `pose` (identity elsewhere) and joint 0 feeds `global`
+    R = torch.from_numpy(gold["edge.R"])                       # [16,4,3,3]
+    L = R.shape[0]
+    vb = synth.make_videos(1, L, seed=6)
+    vb.pose = torch.eye(3).expand(L, 23, 3, 3).clone()
+    vb.pose[:, :4] = R
+    vb.gori = R[:, :1].clone()
+    x = torch.from_numpy(gold["edge.x"])                       # [8,64] -> first 64 vit columns of the first 8 frames
+    vb.vit = torch.zeros(L, 1024)
+    vb.vit[:8, :64] = x
+    vb.vit[8:, 0] = 1.0
+    kp = torch.from_numpy(gold["edge.kp"])                     # [8,120]
+    vb.kp = torch.cat([kp, kp[-1:].expand(L - 8, 120)], 0).clone()
+    dv, fuser = _dv_and_fuser(g, vb)
+    wv = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ws = torch.zeros(1, dtype=torch.int32, device=DEV)
+    feats, flags = fuser.fuse(dv, wv, ws, L, None, None)
+    f = feats[0].cpu()
+    Rd = torch.from_numpy(gold["edge.R_delta"])                # [16,4,3]
+    got_pose = f[:, doff["pose"]:doff["pose"] + 69].reshape(L, 23, 3)
+    assert max_abs(got_pose[:, :4], Rd) < 2e-5                 # theta near pi is ill-conditioned in fp32 (same bar as the oracle)
+    assert float(got_pose[:, 4:].abs().max()) == 0.0           # identity joints -> exactly zero
+    assert float(got_pose[5, :4].abs().max()) < 1e-6           # duplicated frame -> zero rotation
+    assert max_abs(f[:, doff["global"]:doff["global"] + 3], Rd[:, 0]) < 2e-5
+    xd = torch.from_numpy(gold["edge.x_delta"])                # zero row: normalises to zero, no NaN
+    assert max_abs(f[:8, doff["vit"]:doff["vit"] + 64], xd) < 1e-6
+    assert bool(torch.isfinite(f).all())
+    assert max_abs(f[:8, doff["kp2d"]:doff["kp2d"] + 120], gold["edge.kp_delta"]) < 2e-6
+    assert float(f[8:, doff["kp2d"]:doff["kp2d"] + 120].abs().max()) < 1e-6    # repeated last frame -> zero motion
 
 
 # ------------------------------------------------------------------------------------------- N2 stats

@@ -48,6 +48,28 @@ def test_delta_edge_cases(deltas):
     assert max_abs(kc, deltas["edge.kp_delta"]) < 5e-7
 
 
+def test_procrustes_mirror_regime_closed_form():
+    """det(H) < 0 pairs: the closed form (polar-reflection angle) reproduces the reference's SVD path
+    (tests/golden/deltas_mirror.npz, made by the unmodified reference), as does the oracle's own SVD restatement."""
+    gold = np.load(os.path.join(GOLDEN, "deltas_mirror.npz"))
+    for tag in ("iid", "flip"):
+        kp = torch.from_numpy(gold[f"{tag}.kp"])
+        kd, nref = O.procrustes_kp_delta(kp)
+        assert max_abs(kd, gold[f"{tag}.kp_delta"]) < 1e-6
+        kc, det = O.procrustes_kp_delta_closed_form(kp)
+        assert int((det < 0).sum()) == nref and nref >= 10
+        assert max_abs(kc, gold[f"{tag}.kp_delta"]) < 2e-6, tag
+    # 20 k random 2x2 cross-covariances, both regimes, against torch.linalg.svd directly
+    g = torch.Generator().manual_seed(3)
+    worst = 0.0
+    for _ in range(200):
+        kp = torch.rand(101, 120, generator=g)
+        kd, _ = O.procrustes_kp_delta(kp)
+        kc, _ = O.procrustes_kp_delta_closed_form(kp)
+        worst = max(worst, max_abs(kc, kd))
+    assert worst < 5e-6, worst
+
+
 def test_slice_or_pad_index():
     assert O.slice_or_pad_index(10, 2, 4).tolist() == [2, 3, 4, 5]
     assert O.slice_or_pad_index(10, 8, 4).tolist() == [8, 9, 9, 9]          # tail repeats last frame

@@ -7,8 +7,9 @@
 //   utils.py:142-147  _vit_delta        (cosine: L2-normalise, first difference, row 0 = 0)
 //   utils.py:165-174  _rotmat_delta  +  :130-140 _log_so3
 //   utils.py:161-163  _betas_delta
-//   utils.py:177-217  _procrustes_kp_delta (closed form of `Vh @ U.T` for det(H) > 0; det(H) < 0 frames
-//                     are counted in flags[0] — SURVEY.md §8a A6)
+//   utils.py:177-217  _procrustes_kp_delta (closed form of `Vh @ U.T` + det fix-up in both regimes: transposed polar
+//                     rotation for det(H) >= 0, polar-reflection angle for det(H) < 0; the latter frames are also
+//                     counted in flags[0] — SURVEY.md §8a A6)
 //   utils.py:472-514  z-score (x-mean)/(std+1e-6) and concat
 //
 // HBM-bound: per (window, frame) reads sum(raw_dims)*4 B and writes D*4 B (fp32 feats) and/or D16*2 B
@@ -230,13 +231,16 @@ __global__ void __launch_bounds__(kThreads, 4) k_feature_fuse(const FuseParams p
             // H = X^T Y (utils.py:207), X = previous frame, Y = current frame
             const float h00 = warp_sum(px0 * x0 + px1 * x1), h01 = warp_sum(px0 * y0 + px1 * y1);
             const float h10 = warp_sum(py0 * x0 + py1 * x1), h11 = warp_sum(py0 * y0 + py1 * y1);
-            if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
-            // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
-            const float ry = h10 - h01, rx = h00 + h11;
+            const bool mirror = h00 * h11 - h01 * h10 < 0.f;
+            if (mirror && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+            // R = [[c, s], [-s, c]]: angle atan2(h10 - h01, h00 + h11) for det(H) >= 0 (transposed polar rotation), and
+            // atan2(h10 + h01, h00 - h11) for det(H) < 0 (angle of the polar REFLECTION of H: what `Vh @ U.T` plus the
+            // det fix-up of utils.py:209-212 gives with LAPACK's always-improper U); cos and sin are the normalised pair
+            const float ry = mirror ? h10 + h01 : h10 - h01, rx = mirror ? h00 - h11 : h00 + h11;
             const float rr = ry * ry + rx * rx;
             const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
             const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
-            // X @ R with R = [[c, s], [-s, c]]  (== Vh @ U.T for det(H) > 0)
+            // X @ R with R = [[c, s], [-s, c]]
             d00 = x0 - (px0 * cs - py0 * sn); d01 = y0 - (px0 * sn + py0 * cs);
             d10 = x1 - (px1 * cs - py1 * sn); d11 = y1 - (px1 * sn + py1 * cs);
           }
@@ -438,9 +442,12 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
               h00 += __shfl_xor_sync(FULL_MASK, h00, o); h01 += __shfl_xor_sync(FULL_MASK, h01, o);
               h10 += __shfl_xor_sync(FULL_MASK, h10, o); h11 += __shfl_xor_sync(FULL_MASK, h11, o);
             }
-            if (h00 * h11 - h01 * h10 < 0.f && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
-            // R = [[c, s], [-s, c]] with angle atan2(h10 - h01, h00 + h11): cos and sin are just the normalised pair
-            const float ry = h10 - h01, rx = h00 + h11;
+            const bool mirror = h00 * h11 - h01 * h10 < 0.f;
+            if (mirror && lane == 0 && p.flags != nullptr) atomicAdd(p.flags, 1);
+            // R = [[c, s], [-s, c]]: angle atan2(h10 - h01, h00 + h11) for det(H) >= 0 (transposed polar rotation), and
+            // atan2(h10 + h01, h00 - h11) for det(H) < 0 (angle of the polar REFLECTION of H: what `Vh @ U.T` plus the
+            // det fix-up of utils.py:209-212 gives with LAPACK's always-improper U); cos and sin are the normalised pair
+            const float ry = mirror ? h10 + h01 : h10 - h01, rx = mirror ? h00 - h11 : h00 + h11;
             const float rr = ry * ry + rx * rx;
             const float ir = rr > 0.f ? rsqrtf(rr) : 0.f;
             const float cs = rr > 0.f ? rx * ir : 1.f, sn = ry * ir;
