@@ -12,7 +12,12 @@
  *    opaque handle (packed weights + workspace allocated in tag_finalize_weights).
  *  - all work is enqueued asynchronously on the cudaStream_t passed as `void* stream`.
  *  - return 0 on success, a TAG_ERR_* code otherwise; tag_last_error() gives the message.
- *    No exceptions or aborts cross the ABI. A handle is not thread-safe.
+ *    No exceptions or aborts cross the ABI.
+ *  - ONE IN-FLIGHT CALL PER HANDLE: a handle owns mutable state (workspace, z-score tables, error string, launch
+ *    counter), so calls on one handle must be issued from one thread and onto one stream at a time (calls on the
+ *    same stream serialise by themselves). Use one handle per stream / thread for concurrency.
+ *  - tensor-core mode (TAG_PRECISION_FP16_TC) tiles windows into 128-row blocks: clip lengths T must divide 128 or be
+ *    a multiple of 128 (checked up front, TAG_ERR_UNSUPPORTED); TAG_PRECISION_FP32 takes any T.
  *  - all floating point tensors are fp32, row-major, densely packed.
  */
 #ifndef TAG_B200_H
@@ -104,6 +109,9 @@ int tag_feature_fuse(tag_handle* h, const tag_videos* vids, const float* mean, c
  *     (fused, so frame_embeds need not leave the device). */
 int tag_encode(tag_handle* h, const float* feats, int64_t n_windows, int32_t T,
                float* seq_embed, float* frame_embeds, float* tokens, float* tc_window, void* stream);
+/* model.py:94, :185 `last_attn`: the next tag_encode call (only that one) also writes the fusion softmax over modalities,
+ * attn [n_windows*T, M] fp32. NULL switches it off again. */
+int tag_set_fusion_attn_out(tag_handle* h, float* attn);
 
 /* --- K1+K2 fused over windows of resident videos: eval.py:168-206 `extract_window_features`
  *     without materialising feats for all windows (internally chunked by max_windows). */
@@ -154,6 +162,19 @@ int tag_stats_accumulate(tag_handle* h, const float* x, int64_t rows, int32_t D,
  *     one pass; loss_rows [B] (mean over rows = the reference's scalar). targets int32 [B]. */
 int tag_tcl_forward(tag_handle* h, const float* z, const int32_t* targets, int64_t B, float temperature,
                     float k1, float k2, float* loss_rows, void* stream);
+/*     For B >= 512 the similarity matrix Z Z^T is a tcgen05 GEMM (split-fp16 operands hi.hi + lo.hi + hi.lo, fp32
+ *     accumulate: ~1e-7 on S) whose epilogue keeps the masked row sums; the [B,B] matrix never exists in memory.
+ *     targets must not contain INT32_MIN. */
+
+/* --- N1 SupConWithHardNegatives forward (losses.py:37-56): loss_rows [B] = CrossEntropy([a.p/t, a.h/t], 0) per sample
+ *     (mean over rows = the reference's scalar); anchor / positive / hard_negative [B,256]. */
+int tag_supcon_hard_forward(tag_handle* h, const float* anchor, const float* positive, const float* hard_negative,
+                            int64_t B, float temperature, float* loss_rows, void* stream);
+
+/* --- N1 hard-negative augmentations (utils.py:65-95: partial_shuffle_within_window, reverse_sequence, get_static_window)
+ *     are frame gathers: out[b, t, :] = x[b, idx[b*T + t], :], x / out [B, T, D] fp32 (D % 4 == 0), idx int32 [B*T]. */
+int tag_gather_frames(tag_handle* h, const float* x, const int32_t* idx, int64_t B, int32_t T, int32_t D, float* out,
+                      void* stream);
 
 /* --- introspection used by bench.py: kernels launched through this handle since creation; with
  *     profiling on, every encoder kernel is bracketed by CUDA events on the caller's stream and
@@ -162,6 +183,10 @@ int tag_tcl_forward(tag_handle* h, const float* z, const int32_t* targets, int64
 int64_t tag_launch_count(const tag_handle* h);
 int tag_set_profiling(tag_handle* h, int32_t on);
 int tag_get_profile(tag_handle* h, double* out12);
+/* the same split finer: out[3*k .. 3*k+2] = {ms, work, launches} of kind k < n_kinds, k = 0 other, 1 conv GEMM, 2 other GEMM,
+ * 3 feature fuse (K1), 4 merge-fusion (A11 + A12 front half), 5 finalize (A14 + fused per-window TC), 6 attention,
+ * 7 build-tokens (A8); work = FLOPs for the GEMM kinds, ALGORITHMIC BYTES for the bandwidth-bound kinds. */
+int tag_get_profile_kinds(tag_handle* h, double* out, int32_t n_kinds);
 
 /* --- test hooks: the two GEMM kernels in isolation (tests/test_gemm_gpu.py).
  *     C = act(sum_taps A[row+shift] W^T + bias + res); fp32: W [N, ldw]; tensor-core: A/W/res16/C16

@@ -376,7 +376,8 @@ def action_consistency_scores(features: dict, centroids: torch.Tensor, label_dic
 # --------------------------------------------------------------------------------------
 # N1  TCL forward                                                 losses.py:14-34
 # --------------------------------------------------------------------------------------
-def tcl_loss(z: torch.Tensor, targets: torch.Tensor, temperature=0.1, k1=5000.0, k2=1.0) -> torch.Tensor:
+def tcl_loss_rows(z: torch.Tensor, targets: torch.Tensor, temperature=0.1, k1=5000.0, k2=1.0) -> torch.Tensor:
+    """losses.py:14-31, per anchor row (before the final mean of :33)."""
     S = z @ z.T
     E = torch.exp(S / temperature)
     En = torch.exp(-S)
@@ -384,8 +385,43 @@ def tcl_loss(z: torch.Tensor, targets: torch.Tensor, temperature=0.1, k1=5000.0,
     pos = same.to(z.dtype) * (1 - torch.eye(z.shape[0], dtype=z.dtype))
     neg = (~same).to(z.dtype)
     den = (E * pos).sum(1) + k1 * (En * pos).sum(1) + k2 * (E * neg).sum(1)
-    li = (-torch.log(E / den[:, None]) * pos).sum(1) / pos.sum(1)
-    return li.mean()
+    return (-torch.log(E / den[:, None]) * pos).sum(1) / pos.sum(1)
+
+
+def tcl_loss(z: torch.Tensor, targets: torch.Tensor, temperature=0.1, k1=5000.0, k2=1.0) -> torch.Tensor:
+    """losses.py:14-34."""
+    return tcl_loss_rows(z, targets, temperature, k1, k2).mean()
+
+
+def supcon_hard_rows(anchor: torch.Tensor, positive: torch.Tensor, hard_negative: torch.Tensor, temperature=0.07) -> torch.Tensor:
+    """losses.py:43-56 per sample: cross entropy over [a.p/t, a.h/t] with the positive as the target."""
+    sim_ap = (anchor * positive).sum(-1) / temperature
+    sim_ah = (anchor * hard_negative).sum(-1) / temperature
+    logits = torch.stack([sim_ap, sim_ah], dim=1)
+    return F.cross_entropy(logits, torch.zeros(anchor.shape[0], dtype=torch.long), reduction="none")
+
+
+# hard-negative augmentations                                     utils.py:65-95
+def partial_shuffle_within_window(seqs: torch.Tensor, shuffle_fraction: float = 0.7) -> torch.Tensor:
+    """utils.py:65-75 (same RNG consumption: randperm(T)[:n], then randperm(n), per sample)."""
+    out = seqs.clone()
+    B, T, _ = seqs.shape
+    for i in range(B):
+        if T > 1:
+            n = max(1, int(shuffle_fraction * T))
+            idx = torch.randperm(T)[:n]
+            out[i, idx] = out[i, idx][torch.randperm(n)]
+    return out
+
+
+def reverse_sequence(seqs: torch.Tensor) -> torch.Tensor:
+    """utils.py:78-86."""
+    return torch.flip(seqs, dims=[1])
+
+
+def get_static_window(seqs: torch.Tensor) -> torch.Tensor:
+    """utils.py:88-95: every frame replaced by the window's first frame."""
+    return seqs[:, :1].expand_as(seqs).clone()
 
 
 # --------------------------------------------------------------------------------------

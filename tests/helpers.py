@@ -22,6 +22,25 @@ def oracle():
     return importlib.import_module("oracle.tag_oracle")
 
 
+def reference():
+    """The unmodified reference modules from oracle/_ref (placed there by __graft_entry__.build() in the build container; the
+    directory travels to the GPU box) or None."""
+    import sys
+    root = os.path.dirname(HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    rr = importlib.import_module("oracle.ref_runner")
+    return rr.load_ref()
+
+
+def ref_runner():
+    import sys
+    root = os.path.dirname(HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return importlib.import_module("oracle.ref_runner")
+
+
 class GoldenCase:
     def __init__(self, tag):
         self.tag = tag

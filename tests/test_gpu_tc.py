@@ -279,18 +279,34 @@ def test_fused_pipeline_tc_scores():
 
 
 def test_gemm_tc_halo_mode_in_subprocess():
-    """The optional halo-tile conv path (TAG_TC_HALO=2: one activation load per 64-channel chunk, taps as shifted
-    descriptor views, (t, window)-ordered accumulator rows) must give the same results as the default path: re-run the
-    conv GEMM and fused-GroupNorm cases of this file in a child process with the switch set."""
+    """The experimental halo-tile conv path (one activation load per 64-channel chunk, taps as shifted descriptor views,
+    (t, window)-ordered accumulator rows) exists only in the EXPERIMENTS build of the library (libtag_b200_exp.so,
+    -DTAG_EXPERIMENTS; the product library reads no environment variable). It must give the same results as the default path:
+    re-run the conv GEMM and fused-GroupNorm cases of this file in a child process against that build with TAG_TC_HALO=2."""
     import os, subprocess, sys
     if os.environ.get("TAG_TC_HALO"):
         pytest.skip("already inside the halo-mode child")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "video-gen-evals_b200", "libtag_b200_exp.so")):
+        pytest.skip("experiments build not present")
     env = dict(os.environ, TAG_TC_HALO="2")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
-                        "(test_gemm_tc and _t5d) or fused_groupnorm"], env=env, capture_output=True, text=True, timeout=600,
-                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_exp.py"), "-m", "pytest", os.path.abspath(__file__), "-m", "gpu",
+                        "-q", "-x", "-k", "(test_gemm_tc and _t5d) or fused_groupnorm"], env=env, capture_output=True, text=True,
+                       timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+def test_product_library_ignores_experiment_switches():
+    """TAG_TC_DEBUG (which skips loads / stores in the experiments build) must do nothing to the product library."""
+    import os, subprocess, sys
+    if os.environ.get("TAG_TC_DEBUG"):
+        pytest.skip("inside the child")
+    env = dict(os.environ, TAG_TC_DEBUG="7", TAG_TC_HALO="3", TAG_K1_DEBUG="7", TAG_FRAME_TABLE="0", TAG_TC_PAIR="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "fused_pipeline_tc_scores"], env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_score_stream_matches_resident_scores():

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/tag_b200.h but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert tb.load_library().tag_abi_version() == 1
+    assert tb.load_library().tag_abi_version() == 2
 
 
 def test_config_struct_layout_matches_header():

@@ -5,7 +5,7 @@ Public names mirror the reference modules they replace:
   utils.py   -> ModalityStats, WindowDataset, safe_collate, build_train_centroids_subset
   eval.py    -> infer_dims_from_stats, extract_window_features,
                 compute_temporal_coherence_scores, compute_action_consistency_scores
-  losses.py  -> TCL (forward)
+  losses.py  -> TCL, SupConWithHardNegatives (forward); utils.py:65-95 hard-negative augmentations
 plus the fused device-resident pipeline (`TagScorer`) used by bench.py.
 
 Importing the package does not need a GPU; every compute entry point does, and raises `TagError`
@@ -19,7 +19,9 @@ from .features import (ModalityStats, DeviceVideos, FeatureFuser, WindowDataset,
                        infer_dims_from_stats, compute_stats_from_videos)
 from .scoring import (extract_window_features, compute_temporal_coherence_scores,
                       compute_action_consistency_scores, build_train_centroids_subset, centroid_accumulate,
-                      centroid_finalize, allreduce_centroid_sums, TCL, write_video_scores)
+                      centroid_finalize, allreduce_centroid_sums, write_video_scores)
+from .losses import TCL, SupConWithHardNegatives, hard_negative_step
+from .augment import partial_shuffle_within_window, reverse_sequence, get_static_window, gather_frames
 from .pipeline import TagScorer, block_plan, shard_range, window_table
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -50,6 +50,7 @@ SIGNATURES = {
     "tag_finalize_weights": (C.c_int, [_P]),
     "tag_feature_fuse": (C.c_int, [_P, C.POINTER(tag_videos), _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
     "tag_encode": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "tag_set_fusion_attn_out": (C.c_int, [_P, _P]),
     "tag_encode_windows": (C.c_int, [_P, C.POINTER(tag_videos), _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "tag_centroid_accumulate": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "tag_centroid_finalize": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
@@ -57,9 +58,12 @@ SIGNATURES = {
     "tag_window_tc": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
     "tag_stats_accumulate": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
     "tag_tcl_forward": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P, _P]),
+    "tag_supcon_hard_forward": (C.c_int, [_P, _P, _P, _P, _I64, _F, _P, _P]),
+    "tag_gather_frames": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _P, _P]),
     "tag_launch_count": (_I64, [_P]),
     "tag_set_profiling": (C.c_int, [_P, _I32]),
     "tag_get_profile": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "tag_get_profile_kinds": (C.c_int, [_P, C.POINTER(C.c_double), _I32]),
     "tag_debug_gemm_f32": (C.c_int, [_P, _P, _I32, _P, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _I32, _P]),
     "tag_encode_clips": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "tag_debug_feature_fuse16": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),

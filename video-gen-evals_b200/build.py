@@ -34,18 +34,23 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments=True builds libtag_b200_exp.so with -DTAG_EXPERIMENTS: the bottleneck switches (TAG_TC_DEBUG,
+    TAG_TC_HALO, TAG_TC_PAIR, TAG_K1_DEBUG, TAG_FRAME_TABLE environment variables) exist only there, for tools/;
+    the product library reads no environment variable."""
+    OBJ = os.path.join(HERE, "build_exp" if experiments else "build")
+    LIB = os.path.join(HERE, "libtag_b200_exp.so" if experiments else "libtag_b200.so")
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "tag_b200.h"))
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DTAG_EXPERIMENTS"] if experiments else [])
 
     def compile_one(src):
         sp = os.path.join(CSRC, src)
         op = os.path.join(OBJ, src.replace(".cu", ".o"))
         stamp = op + ".sha"
-        dg = _digest([sp] + headers)
+        dg = _digest([sp] + headers) + ("exp" if experiments else "")
         if not force and os.path.exists(op) and os.path.exists(stamp) and open(stamp).read() == dg:
             return op, ""
         cmd = [nvcc] + flags + ["-c", sp, "-o", op]
@@ -72,4 +77,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, experiments="--experiments" in sys.argv))

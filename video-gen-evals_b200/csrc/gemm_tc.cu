@@ -98,6 +98,12 @@ struct TcParams {
   const float* gn_beta;
   const float* ln_gamma;   // MODE 2 only: LayerNorm over the 256 output columns (N == 256), fused after bias + residual;
   const float* ln_beta;    //   writes the fp32 stream (C32, may alias res32) and its fp16 copy (C16)
+  // MODE 3 only (TCL forward, losses.py:14-34): the accumulator is the similarity tile S = Z Z^T; the epilogue keeps five masked
+  // row sums per (row, 64-column slice) instead of storing S
+  const int32_t* tcl_y;    // [M] class of every embedding (rows and columns index the same batch)
+  float* tcl_part;         // [M][N / 64][5]: sum_pos exp(S/t), sum_pos exp(-S), sum_neg exp(S/t), sum_pos S/t, #pos
+  float tcl_inv_temp;
+  int tcl_valid;           // columns >= tcl_valid are padding (N rounded up to 256)
   int dbg;                 // bottleneck experiments (TAG_TC_DEBUG): 1 no epilogue stores, 2 no weight loads, 4 no activation loads
   // halo mode (conv): A chunk loaded once per 64 channels with its time halo, taps = shifted descriptor views
   int halo;                // 0 off, 1 on, 2 on with the descriptor base-offset field set for unaligned tap shifts (experiment)
@@ -391,6 +397,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   const bool leader = rank == 0;
   constexpr bool GN = MODE == 1;
   constexpr bool LN = MODE == 2;
+  constexpr bool TCL = MODE == 3;
   // barrier slots (8 B each, layout at MAX_BARS); then the TMEM base word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -811,6 +818,46 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             __syncwarp();
           }
         }
+      } else if constexpr (TCL) {
+        // ---- TCL forward: masked row sums of the similarity tile (lane = anchor row i, columns = the other embeddings j)
+        const int64_t i = tile_row(rm.tile_base, rm.rt0 + lane, rm.lw, rm.lt);
+        constexpr int kPadLabel = (int)0x80000000;                        // INT_MIN never is a class
+        const int yi = i < p.M ? __ldg(p.tcl_y + i) : kPadLabel;
+        // classes of this warp's 64 columns: two per lane, broadcast by shuffle below
+        const int j0 = n_base + lane, j1 = n_base + 32 + lane;
+        const int ya = j0 < p.tcl_valid ? __ldg(p.tcl_y + j0) : kPadLabel;
+        const int yb = j1 < p.tcl_valid ? __ldg(p.tcl_y + j1) : kPadLabel;
+        float e_pos = 0.f, en_pos = 0.f, e_neg = 0.f, s_pos = 0.f, n_pos = 0.f;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
+          tmem_ld16_wait(raw);
+          if (c == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+          }
+#pragma unroll
+          for (int e = 0; e < CW; ++e) {
+            const int col = c * CW + e;                                   // 0..63 inside the warp's slice
+            const int yj = __shfl_sync(FULL_MASK, col < 32 ? ya : yb, col & 31);
+            const float sv = __uint_as_float(raw[e]);
+            const float st = sv * p.tcl_inv_temp;
+            const float ex = __expf(st);
+            if (yj == yi) {
+              if ((int64_t)(n_base + col) != i) { e_pos += ex; en_pos += __expf(-sv); s_pos += st; n_pos += 1.f; }
+            } else if (yj != kPadLabel) {
+              e_neg += ex;
+            }
+          }
+        }
+        if (i < p.M) {
+          float* o = p.tcl_part + ((size_t)i * (size_t)(p.N / EPI_COLS) + (size_t)(n_base / EPI_COLS)) * 5;
+          o[0] = e_pos; o[1] = en_pos; o[2] = e_neg; o[3] = s_pos; o[4] = n_pos;
+        }
       } else if (!out32) {
         // ---- fp16 output (optional fp16 residual): 2 units of 32 columns
         const bool has_res = p.res16 != nullptr;
@@ -942,12 +989,16 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+#ifdef TAG_EXPERIMENTS   // tools/ build only (build.py --experiments -> libtag_b200_exp.so): the product library reads no environment
   const char* env = getenv("TAG_TC_PAIR");
   if (env != nullptr) c->pair = env[0] != '0';
   env = getenv("TAG_TC_DEBUG");
   if (env != nullptr) c->dbg = atoi(env);
   env = getenv("TAG_TC_HALO");
   if (env != nullptr) c->halo = atoi(env);
+#endif
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
     delete c;
@@ -974,6 +1025,12 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
                           ((reinterpret_cast<uintptr_t>(g.A2) - reinterpret_cast<uintptr_t>(g.A)) & 15)))
     return bad("a second K segment needs a plain GEMM and a second activation tensor of the same shape and row pitch");
   const bool ln = g.ln_gamma != nullptr;
+  const bool tcl = g.tcl_part != nullptr;
+  if (tcl) {
+    if (g.tcl_y == nullptr || g.taps != 1 || g.C16 != nullptr || g.C32 != nullptr || g.res16 != nullptr || g.res32 != nullptr ||
+        g.bias != nullptr || g.gn_gamma != nullptr || ln || g.A2 != nullptr || g.g_L > 0 || g.tcl_valid < 1 || g.tcl_valid > g.N)
+      return bad("the TCL epilogue needs a plain GEMM without outputs, bias or residual");
+  } else
   if (ln) {
     if (g.ln_beta == nullptr || g.taps != 1 || g.N != BLOCK_N || g.C16 == nullptr || g.C32 == nullptr || g.res32 == nullptr ||
         g.res16 != nullptr || g.gn_gamma != nullptr || g.act != 0)
@@ -994,6 +1051,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
   p.bias = g.bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
   p.gn_gamma = g.gn_gamma; p.gn_beta = g.gn_beta;
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta;
+  p.tcl_y = g.tcl_y; p.tcl_part = g.tcl_part; p.tcl_inv_temp = g.tcl_inv_temp; p.tcl_valid = g.tcl_valid;
   p.dbg = ctx->dbg;
   const bool gn = g.gn_gamma != nullptr;
   if (gn) {
@@ -1111,13 +1169,15 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (tcl) return cudaLaunchKernelEx(&cfg, k_gemm_tc<3, true>, map_a, map_b, p);
     if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<1, true>, map_a, map_b, p);
     if (ln) return cudaLaunchKernelEx(&cfg, k_gemm_tc<2, true>, map_a, map_b, p);
     return cudaLaunchKernelEx(&cfg, k_gemm_tc<0, true>, map_a, map_b, p);
   }
   const int64_t total = p.m_tiles * p.n_tiles;
   const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
-  if (gn) k_gemm_tc<1, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  if (tcl) k_gemm_tc<3, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  else if (gn) k_gemm_tc<1, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
   else if (ln) k_gemm_tc<2, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
   else k_gemm_tc<0, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
   return cudaGetLastError();

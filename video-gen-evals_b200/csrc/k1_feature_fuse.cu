@@ -679,8 +679,12 @@ cudaError_t launch_feature_fuse(const FuseParams& p, cudaStream_t s) {
           configured = smem_total;
         }
         const int64_t blocks = p.n_windows * pl.bpw;
+#ifdef TAG_EXPERIMENTS
         static int dbg = -1;
-        if (dbg < 0) { const char* e = getenv("TAG_K1_DEBUG"); dbg = e ? atoi(e) : 0; }   // bottleneck experiments only
+        if (dbg < 0) { const char* e = getenv("TAG_K1_DEBUG"); dbg = e ? atoi(e) : 0; }   // bottleneck experiments (tools/ build only)
+#else
+        const int dbg = 0;
+#endif
         if (p.T % kS == 0) k_feature_fuse_staged<kS, true><<<(unsigned)blocks, 256, smem_total, s>>>(p, pl, dbg);
         else k_feature_fuse_staged<kS, false><<<(unsigned)blocks, 256, smem_total, s>>>(p, pl, dbg);
         return cudaGetLastError();

@@ -37,14 +37,25 @@ inline int feature_fuse_launches(const FuseParams& p) {
 }
 
 // ------------------------------------------------------------------ K3 / K4 / N1 / N2
+// deterministic two-pass K3; `scratch` holds centroid_scratch_floats(n, C) floats (per-CTA partial sums)
+size_t centroid_scratch_floats(int64_t n, int C);
 cudaError_t launch_centroid_accumulate(const float* z, const int32_t* labels, int64_t n, int C,
-                                       float* sums_counts, cudaStream_t s);
+                                       float* sums_counts, float* scratch, cudaStream_t s);
 cudaError_t launch_centroid_finalize(const float* sums_counts, int C, float* centroids, float* counts, cudaStream_t s);
 cudaError_t launch_score(const float* seq, const float* tcw, const int64_t* seg, const int32_t* label,
                          const float* cen, int C, int64_t V, float* ac, float* tc, cudaStream_t s);
 cudaError_t launch_stats_accumulate(const float* x, int64_t rows, int D, double* sum, double* sumsq, cudaStream_t s);
 cudaError_t launch_tcl_forward(const float* z, const int32_t* y, int64_t B, float temperature, float k1, float k2,
                                float* loss_rows, cudaStream_t s);
+// tensor-core TCL: z [B,256] fp32 -> split-fp16 operands A = [hi | lo | hi], W = [hi | hi | lo] ([Bp, 768], rows >= B zero), so
+// that A W^T = hi.hi + lo.hi + hi.lo = Z Z^T to ~1e-7; then the row sums of tcl_part -> loss_rows
+cudaError_t launch_tcl_split(const float* z, int64_t B, int64_t Bp, __half* A, __half* W, cudaStream_t s);
+cudaError_t launch_tcl_finish(const float* part, int64_t B, int slices, float k1, float k2, float* loss_rows, cudaStream_t s);
+// SupConWithHardNegatives forward (losses.py:37-56): rows [B] of softplus((a.h - a.p) / temperature)
+cudaError_t launch_supcon_hard(const float* anchor, const float* positive, const float* hard, int64_t B, float temperature,
+                               float* loss_rows, cudaStream_t s);
+// out[b, t, :] = x[b, idx[b*T + t], :] (hard-negative augmentations, utils.py:65-95); D % 4 == 0
+cudaError_t launch_gather_frames(const float* x, const int32_t* idx, int64_t B, int T, int D, float* out, cudaStream_t s);
 
 // ------------------------------------------------------------------ encoder building blocks
 // Generic fp32 CUDA-core GEMM with conv taps:  C[M,N] = act( sum_j A[row+shift_j, :K] . W[n, j*K : (j+1)*K] + bias + res )
@@ -122,6 +133,9 @@ struct GemmTC {
   // zero motion whatever the table holds).
   int g_L, g_wpv, g_stride; int64_t g_rows;
   const float* row0_vec;
+  // TCL forward (losses.py:14-34): C = Z Z^T is never stored; the epilogue keeps, per row and per 64-column slice, the five masked
+  // sums {sum_pos exp(S/t), sum_pos exp(-S), sum_neg exp(S/t), sum_pos S/t, #pos} in tcl_part [M][N/64][5] (all outputs null)
+  const int32_t* tcl_y; float* tcl_part; float tcl_inv_temp; int tcl_valid;
 };
 struct TcContext;   // opaque: driver entry points + cached tensor maps
 TcContext* tc_context_create(int device, char* err, int errlen);

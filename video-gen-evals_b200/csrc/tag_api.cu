@@ -36,7 +36,10 @@ struct LayerWeights {               // nn.TransformerEncoderLayer (model.py:145)
   __half *in_w16, *out_w16, *l1_w16, *l2_w16;
 };
 
-struct ProfEvent { cudaEvent_t a, b; double flops; int kind; };   // kind: 0 other, 1 conv GEMM, 2 other GEMM, 3 feature fuse (K1)
+// kind: 0 other, 1 conv GEMM, 2 other GEMM, 3 feature fuse (K1), 4 merge-fusion, 5 finalize (+ per-window TC), 6 attention,
+// 7 build-tokens; `flops` = FLOPs for the GEMM kinds, algorithmic bytes for the bandwidth-bound kinds
+constexpr int kProfKinds = 8;
+struct ProfEvent { cudaEvent_t a, b; double flops; int kind; };
 
 }  // namespace
 
@@ -73,7 +76,7 @@ struct tag_handle {
   bool profiling = false;
   std::vector<ProfEvent> prof;
   size_t prof_used = 0;
-  double prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per kind: ms, flops (K1: bytes), launches
+  double prof_acc[3 * kProfKinds] = {};   // per kind: ms, flops (bandwidth-bound kinds: bytes), launches
   int* col_tab = nullptr;           // device [M][6] column map fp32 feats -> fp16 operand layout
   float* zs_scale = nullptr;        // [D] z-score tables, rebuilt from (mean, std) at every feature-fuse call
   float* zs_shift = nullptr;
@@ -82,7 +85,13 @@ struct tag_handle {
   int32_t* zeros = nullptr;         // [max_windows] 0
   int32_t *clip_wv = nullptr, *clip_ws = nullptr;   // [max_windows] window table of one pass (fallback path)
   float* row0 = nullptr;            // [M][256]: motion stem applied to the z-scored zero difference
-  int frame_table = 1;              // TAG_FRAME_TABLE=0 disables the mode (A/B)
+  int frame_table = 1;              // frame-table mode of tag_encode_clips (TAG_FRAME_TABLE=0 disables it in TAG_EXPERIMENTS builds)
+  float* attn_out = nullptr;        // tag_set_fusion_attn_out: [rows, M] fusion softmax of the NEXT tag_encode call (model.py:94 last_attn)
+  __half *tcl_A = nullptr, *tcl_W = nullptr;   // tensor-core TCL: split-fp16 operands [Bp, 768] and the per-slice partial sums
+  float* tcl_part = nullptr;
+  int64_t tcl_cap = 0;              // rows (Bp) the three buffers are sized for
+  float* k3_scratch = nullptr;      // per-CTA partial sums of the deterministic centroid reduction (grown on demand)
+  size_t k3_scratch_floats = 0;
 };
 
 namespace {
@@ -247,7 +256,7 @@ int gemm_tc_run(tag_handle* h, cudaStream_t s, const GemmTC& g, double flops) {
 
 // ---- fp32 mode ----------------------------------------------------------------------------------
 int encode_chunk_f32(tag_handle* h, cudaStream_t s, const float* feats, int64_t W, int T, float* seq, float* frame,
-                     float* tokens, float* tcw) {
+                     float* tokens, float* tcw, float* attn = nullptr) {
   const int64_t R = W * T, R2 = W * (T + 1);
   const int M = h->M;
   float* bufH = (float*)h->bufH; float* bufY1 = (float*)h->bufY1; float* bufY2 = (float*)h->bufY2;
@@ -280,8 +289,8 @@ int encode_chunk_f32(tag_handle* h, cudaStream_t s, const float* feats, int64_t 
     mp.inv_tau[m] = h->inv_tau[m];
     mp.lbias[m] = h->lbias[m];
   }
-  mp.kv_gamma = h->kv_g; mp.kv_beta = h->kv_b; mp.qk = h->qk; mp.mix = h->mix; mp.attn = nullptr; mp.R = R;
-  { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_merge_fusion<float>(mp, s)); }
+  mp.kv_gamma = h->kv_g; mp.kv_beta = h->kv_b; mp.qk = h->qk; mp.mix = h->mix; mp.attn = attn; mp.R = R;
+  { ProfScope ps(h, s, 4, (double)R * (2 * M + 1) * kD * 4); LAUNCH_TRY(h, launch_merge_fusion<float>(mp, s)); }
   float* fusedA = (float*)h->fusedA; float* fusedB = (float*)h->fusedB;
   rc = Gemm<float>::run(h, s, (const float*)h->mix, kD, h->Wv, kD, R, kD, kD, 1, 1, T, nullptr, nullptr, fusedA, 0);
   if (rc) return rc;
@@ -313,7 +322,7 @@ int encode_chunk_f32(tag_handle* h, cudaStream_t s, const float* feats, int64_t 
 struct ClipGather { int L = 0, wpv = 0, stride = 0; int64_t rows = 0; };
 
 int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_t W, int T, float* seq, float* frame,
-                    float* tokens, float* tcw, const ClipGather* cg = nullptr) {
+                    float* tokens, float* tcw, const ClipGather* cg = nullptr, float* attn = nullptr) {
   const int64_t R = W * T, R2 = W * (T + 1);
   const int M = h->M;
   __half* bufY1 = (__half*)h->bufY1; __half* bufY2 = (__half*)h->bufY2;
@@ -374,8 +383,8 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
     mp.inv_tau[m] = h->inv_tau[m];
     mp.lbias[m] = h->lbias[m];
   }
-  mp.kv_gamma = h->kv_g; mp.kv_beta = h->kv_b; mp.qk = h->qk; mp.mix = h->mix; mp.attn = nullptr; mp.R = R;
-  { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_merge_fusion<__half>(mp, s)); }
+  mp.kv_gamma = h->kv_g; mp.kv_beta = h->kv_b; mp.qk = h->qk; mp.mix = h->mix; mp.attn = attn; mp.R = R;
+  { ProfScope ps(h, s, 4, (double)R * (M + 1) * kD * 2); LAUNCH_TRY(h, launch_merge_fusion<__half>(mp, s)); }
   __half* fused = (__half*)h->fusedA;
   {
     GemmTC g{};
@@ -385,7 +394,7 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
     rc = gemm_tc_run(h, s, g, 2.0 * R * kD * kD); if (rc) return rc;
   }
   __half* X16 = (__half*)h->X16;
-  { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_build_tokens<__half>(fused, h->cls, h->pe, h->X, X16, W, T, s)); }
+  { ProfScope ps(h, s, 7, (double)R * kD * 2 + (double)R2 * kD * 6); LAUNCH_TRY(h, launch_build_tokens<__half>(fused, h->cls, h->pe, h->X, X16, W, T, s)); }
   __half* QKV = (__half*)h->QKV; __half* ATT = (__half*)h->ATT; __half* FF = (__half*)h->FF;
   const int F = h->cfg.ffn_dim;
   for (const LayerWeights& L : h->layers) {
@@ -393,7 +402,7 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
     q.A = X16; q.M = R2; q.lda = kD; q.W = L.in_w16; q.N = 3 * kD; q.K = kD; q.taps = 1; q.dil = 1; q.T = 1; q.bias = L.in_b;
     q.C16 = QKV; q.ldc = 3 * kD;
     rc = gemm_tc_run(h, s, q, 2.0 * R2 * 3 * kD * kD); if (rc) return rc;
-    { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_attention<__half>(QKV, ATT, W, T + 1, h->cfg.n_heads, s)); }
+    { ProfScope ps(h, s, 6, (double)R2 * kD * 8); LAUNCH_TRY(h, launch_attention<__half>(QKV, ATT, W, T + 1, h->cfg.n_heads, s)); }
     GemmTC o{};
     o.A = ATT; o.M = R2; o.lda = kD; o.W = L.out_w16; o.N = kD; o.K = kD; o.taps = 1; o.dil = 1; o.T = 1; o.bias = L.out_b;
     // out-proj + bias + residual + LayerNorm(norm1) in one kernel, in place over the fp32 token stream
@@ -408,7 +417,11 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
     f2.res32 = h->X; f2.C32 = h->X; f2.C16 = X16; f2.ldc = kD; f2.ln_gamma = L.n2_g; f2.ln_beta = L.n2_b;
     rc = gemm_tc_run(h, s, f2, 2.0 * R2 * F * kD); if (rc) return rc;
   }
-  { ProfScope ps(h, s, 0, 0); LAUNCH_TRY(h, launch_finalize(h->X, W, T + 1, seq, frame, tokens, tcw, s)); }
+  {
+    // algorithmic bytes: the fp32 token stream in, seq embeds (+ frame embeds / tokens when asked for) and the window TC out
+    const double bytes = (double)R2 * kD * 4 * (1 + (frame ? 1 : 0) + (tokens ? 1 : 0)) + (double)W * (kD * 4 + 4);
+    ProfScope ps(h, s, 5, bytes); LAUNCH_TRY(h, launch_finalize(h->X, W, T + 1, seq, frame, tokens, tcw, s));
+  }
   return TAG_OK;
 }
 
@@ -434,6 +447,9 @@ int check_common(tag_handle* h, int64_t n_windows, int T) {
   if (n_windows < 0) return fail(h, TAG_ERR_INVALID, "n_windows < 0");
   if (T < 1 || T > h->cfg.max_T) return fail(h, TAG_ERR_INVALID, "T=%d outside [1, max_T=%d]", T, h->cfg.max_T);
   if (T + 1 > h->pe_rows) return fail(h, TAG_ERR_INVALID, "T+1=%d exceeds the positional table (%d rows)", T + 1, h->pe_rows);
+  if (h->cfg.precision == TAG_PRECISION_FP16_TC && !((T <= 128 && 128 % T == 0) || T % 128 == 0))
+    return fail(h, TAG_ERR_UNSUPPORTED, "clip length T=%d: the tensor-core mode tiles windows into 128-row blocks and needs T dividing 128 "
+                "(1, 2, 4, ..., 128) or a multiple of 128; use precision fp32 (TAG_PRECISION_FP32) for other clip lengths", T);
   return TAG_OK;
 }
 
@@ -509,7 +525,7 @@ int fill_fuse_params(tag_handle* h, FuseParams* p, const tag_videos* vids, const
 // =================================================================================================
 extern "C" {
 
-int tag_abi_version(void) { return 1; }
+int tag_abi_version(void) { return 2; }
 
 const char* tag_last_error(const tag_handle* h) { return h ? h->err : g_create_error; }
 
@@ -570,6 +586,10 @@ void tag_destroy(tag_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->k3_scratch) cudaFree(h->k3_scratch);
+  if (h->tcl_A) cudaFree(h->tcl_A);
+  if (h->tcl_W) cudaFree(h->tcl_W);
+  if (h->tcl_part) cudaFree(h->tcl_part);
   for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (h->tc) tc_context_destroy(h->tc);
   delete h;
@@ -732,8 +752,10 @@ int tag_finalize_weights(tag_handle* h) {
     k_iota_zero<<<(mw + 255) / 256, 256>>>(h->iota, h->zeros, mw);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaDeviceSynchronize());
+#ifdef TAG_EXPERIMENTS
     const char* env = getenv("TAG_FRAME_TABLE");
     if (env != nullptr) h->frame_table = atoi(env);
+#endif
   } else {
     if ((rc = dev_alloc(h, &h->feats, R * h->D))) return rc;
   }
@@ -782,6 +804,12 @@ int tag_debug_feature_fuse16(tag_handle* h, const tag_videos* vids, const float*
   return TAG_OK;
 }
 
+int tag_set_fusion_attn_out(tag_handle* h, float* attn) {
+  if (!h) return TAG_ERR_INVALID;
+  h->attn_out = attn;
+  return TAG_OK;
+}
+
 int tag_encode(tag_handle* h, const float* feats, int64_t n_windows, int32_t T, float* seq_embed, float* frame_embeds,
                float* tokens, float* tc_window, void* stream) {
   int rc = check_common(h, n_windows, T);
@@ -801,16 +829,18 @@ int tag_encode(tag_handle* h, const float* feats, int64_t n_windows, int32_t T, 
     float* tk = tokens ? tokens + w0 * S * kD : nullptr;
     float* tw = tc_window ? tc_window + w0 : nullptr;
     const float* f = feats + w0 * (int64_t)T * h->D;
+    float* at = h->attn_out ? h->attn_out + w0 * (int64_t)T * h->M : nullptr;
     if (tc) {
       k_feats_to_half<<<(unsigned)(W * T), 256, 0, s>>>(f, h->feats16, W * T, h->D, h->D16, h->M, tab);
       h->launches++;
       CUDA_TRY(h, cudaGetLastError());
-      rc = encode_chunk_tc(h, s, h->feats16, W, T, seq, fr, tk, tw);
+      rc = encode_chunk_tc(h, s, h->feats16, W, T, seq, fr, tk, tw, nullptr, at);
     } else {
-      rc = encode_chunk_f32(h, s, f, W, T, seq, fr, tk, tw);
+      rc = encode_chunk_f32(h, s, f, W, T, seq, fr, tk, tw, at);
     }
     if (rc) break;
   }
+  h->attn_out = nullptr;                       // one-shot: applies to this call only
   if (rc) return rc;
   return prof_end(h, s);
 }
@@ -928,7 +958,18 @@ int tag_centroid_accumulate(tag_handle* h, const float* z, const int32_t* labels
   if (n == 0) return TAG_OK;
   if (!z || !labels || !sums_counts) return fail(h, TAG_ERR_INVALID, "tag_centroid_accumulate: NULL argument");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  LAUNCH_TRY(h, launch_centroid_accumulate(z, labels, n, C, sums_counts, (cudaStream_t)stream));
+  const size_t need = centroid_scratch_floats(n, C);
+  if (need > h->k3_scratch_floats) {          // rare: the first call, or a larger (n, C) than any before
+    if (h->k3_scratch != nullptr) {
+      CUDA_TRY(h, cudaDeviceSynchronize());   // earlier launches may still read the old buffer
+      CUDA_TRY(h, cudaFree(h->k3_scratch));
+      h->k3_scratch = nullptr; h->k3_scratch_floats = 0;
+    }
+    CUDA_TRY(h, cudaMalloc((void**)&h->k3_scratch, need * sizeof(float)));
+    h->k3_scratch_floats = need;
+  }
+  LAUNCH_TRY(h, launch_centroid_accumulate(z, labels, n, C, sums_counts, h->k3_scratch, (cudaStream_t)stream));
+  h->launches++;                              // two kernels: per-CTA partials, then the fixed-order combine
   return TAG_OK;
 }
 
@@ -982,7 +1023,59 @@ int tag_tcl_forward(tag_handle* h, const float* z, const int32_t* targets, int64
   if (B == 0) return TAG_OK;
   if (!z || !targets || !loss_rows) return fail(h, TAG_ERR_INVALID, "tag_tcl_forward: NULL argument");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-  LAUNCH_TRY(h, launch_tcl_forward(z, targets, B, temperature, k1, k2, loss_rows, (cudaStream_t)stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B < 512) {            // a handful of tiles: one warp per anchor row on the CUDA cores (fp32 dot products)
+    LAUNCH_TRY(h, launch_tcl_forward(z, targets, B, temperature, k1, k2, loss_rows, s));
+    return TAG_OK;
+  }
+  // Z Z^T on the tensor cores (tcgen05, split-fp16 operands: hi.hi + lo.hi + hi.lo, fp32 accumulate), the masked row sums in
+  // the GEMM epilogue — the [B,B] similarity matrix never exists in memory
+  if (!h->tc) {
+    h->tc = tc_context_create(h->cfg.device, h->err, 512);
+    if (!h->tc) return TAG_ERR_CUDA;
+  }
+  const int64_t Bp = (B + 255) / 256 * 256;
+  if (Bp > h->tcl_cap) {
+    if (h->tcl_cap) CUDA_TRY(h, cudaDeviceSynchronize());
+    if (h->tcl_A) cudaFree(h->tcl_A);
+    if (h->tcl_W) cudaFree(h->tcl_W);
+    if (h->tcl_part) cudaFree(h->tcl_part);
+    h->tcl_A = h->tcl_W = nullptr; h->tcl_part = nullptr; h->tcl_cap = 0;
+    CUDA_TRY(h, cudaMalloc((void**)&h->tcl_A, (size_t)Bp * 3 * kD * sizeof(__half)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->tcl_W, (size_t)Bp * 3 * kD * sizeof(__half)));
+    CUDA_TRY(h, cudaMalloc((void**)&h->tcl_part, (size_t)Bp * (size_t)(Bp / 64) * 5 * sizeof(float)));
+    h->tcl_cap = Bp;
+  }
+  LAUNCH_TRY(h, launch_tcl_split(z, B, Bp, h->tcl_A, h->tcl_W, s));
+  GemmTC g{};
+  g.A = h->tcl_A; g.M = B; g.lda = 3 * kD; g.W = h->tcl_W; g.N = (int)Bp; g.K = 3 * kD; g.taps = 1; g.dil = 1; g.T = 1;
+  g.tcl_y = targets; g.tcl_part = h->tcl_part; g.tcl_inv_temp = 1.0f / temperature; g.tcl_valid = (int)B;
+  h->err[0] = 0;
+  int rc = gemm_tc_run(h, s, g, 2.0 * (double)B * (double)B * kD);
+  if (rc) return rc;
+  LAUNCH_TRY(h, launch_tcl_finish(h->tcl_part, B, (int)(Bp / 64), k1, k2, loss_rows, s));
+  return TAG_OK;
+}
+
+int tag_supcon_hard_forward(tag_handle* h, const float* anchor, const float* positive, const float* hard_negative, int64_t B,
+                            float temperature, float* loss_rows, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  if (B < 0 || temperature <= 0.f) return fail(h, TAG_ERR_INVALID, "B=%lld temperature=%f", (long long)B, temperature);
+  if (B == 0) return TAG_OK;
+  if (!anchor || !positive || !hard_negative || !loss_rows) return fail(h, TAG_ERR_INVALID, "tag_supcon_hard_forward: NULL argument");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  LAUNCH_TRY(h, launch_supcon_hard(anchor, positive, hard_negative, B, temperature, loss_rows, (cudaStream_t)stream));
+  return TAG_OK;
+}
+
+int tag_gather_frames(tag_handle* h, const float* x, const int32_t* idx, int64_t B, int32_t T, int32_t D, float* out, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  if (B < 0 || T < 1 || D < 4 || D % 4) return fail(h, TAG_ERR_INVALID, "B=%lld T=%d D=%d (D must be a multiple of 4)", (long long)B, T, D);
+  if (B == 0) return TAG_OK;
+  if (!x || !idx || !out || x == out) return fail(h, TAG_ERR_INVALID, "tag_gather_frames: NULL argument or in-place call");
+  if (B * (int64_t)T >= (1ll << 31)) return fail(h, TAG_ERR_INVALID, "tag_gather_frames: B*T too large");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  LAUNCH_TRY(h, launch_gather_frames(x, idx, B, T, D, out, (cudaStream_t)stream));
   return TAG_OK;
 }
 
@@ -1028,12 +1121,22 @@ int tag_set_profiling(tag_handle* h, int32_t on) {
 }
 
 int tag_get_profile(tag_handle* h, double* out12) {
-  double* out9 = out12;
-  if (!h || !out9) return TAG_ERR_INVALID;
+  if (!h || !out12) return TAG_ERR_INVALID;
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = prof_collect(h);
   if (rc) return rc;
-  for (int i = 0; i < 12; ++i) out9[i] = h->prof_acc[i];
+  for (int i = 0; i < 12; ++i) out12[i] = h->prof_acc[i];
+  for (int k = 4; k < kProfKinds; ++k) { out12[0] += h->prof_acc[3 * k]; out12[2] += h->prof_acc[3 * k + 2]; }   // "other" = every non-GEMM, non-K1 kernel
+  return TAG_OK;
+}
+
+int tag_get_profile_kinds(tag_handle* h, double* out, int32_t n_kinds) {
+  if (!h || !out || n_kinds < 1) return TAG_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  int rc = prof_collect(h);
+  if (rc) return rc;
+  for (int k = 0; k < n_kinds; ++k)
+    for (int j = 0; j < 3; ++j) out[3 * k + j] = k < kProfKinds ? h->prof_acc[3 * k + j] : 0.0;
   return TAG_OK;
 }
 

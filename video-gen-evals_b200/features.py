@@ -235,7 +235,7 @@ class WindowDataset:
         self.fuser = fuser or FeatureFuser(dims_map_raw, dims_map_diff, videos.device)
         self.stats = stats
         self.mean, self.std = stats_vectors(stats, self.fuser.modalities, videos.device)
-        self.reflect_frames = 0
+        self._flags_acc = None
 
     @classmethod
     def all_windows(cls, videos: DeviceVideos, clip_len: int = 32, stride: int = 8, **kw) -> "WindowDataset":
@@ -252,7 +252,15 @@ class WindowDataset:
         ws = torch.tensor([self.samples[i][1] for i in idx], dtype=torch.int32, device=dev)
         feats, flags = self.fuser.fuse(self.videos, wv, ws, self.clip_len, self.mean, self.std)
         self._last_flags = flags
+        self._flags_acc = flags if self._flags_acc is None else self._flags_acc + flags      # on the device: no sync here
         return feats
+
+    @property
+    def reflect_frames(self) -> int:
+        """Frames (over all windows built so far) whose keypoint cross-covariance had det(H) < 0 — mirror-like consecutive
+        frames, e.g. a detector's left/right swap. K1 reproduces the reference there too (polar-reflection closed form);
+        the count is informational (a high count usually means noisy keypoints). Reading it synchronises."""
+        return 0 if self._flags_acc is None else int(self._flags_acc.item())
 
     def __getitem__(self, i: int):
         v, _ = self.samples[i]

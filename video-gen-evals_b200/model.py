@@ -231,11 +231,13 @@ class HumanActionScorer(nn.Module):
         seq = torch.empty(B, self.d_model, device=x.device, dtype=torch.float32)
         frames = torch.empty(B, Tn + 1, self.d_model, device=x.device, dtype=torch.float32)
         tokens = torch.empty(B, Tn + 1, self.d_model, device=x.device, dtype=torch.float32)
+        attn = torch.empty(B * Tn, self.M, device=x.device, dtype=torch.float32)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
+            _lib.check(h, lib.tag_set_fusion_attn_out(h, attn.data_ptr()), "tag_set_fusion_attn_out")
             _lib.check(h, lib.tag_encode(h, x.data_ptr(), B, Tn, seq.data_ptr(), frames.data_ptr(), tokens.data_ptr(),
                                          None, stream), "tag_encode")
-        self.last_attn = None      # reference keeps the fusion softmax for debugging only (model.py:94, :185)
+        self.last_attn = attn      # [B*T, M] fusion softmax, as the reference keeps it (model.py:94, :185)
         return seq, frames, tokens
 
     def launch_count(self) -> int:

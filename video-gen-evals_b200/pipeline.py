@@ -185,17 +185,21 @@ class TagScorer:
 
         def jobs():
             for b, vb in enumerate(batches):
+                if vb.n_videos == 0:                          # an empty batch still gets its (empty) result, in order
+                    yield vb, 0, 0, True, 0
+                    continue
                 if pieces is None:
                     plan = self._block_plan([vb.length(v) for v in range(vb.n_videos)], first=(b == 0))
                 else:
                     n = max(1, min(int(pieces), vb.n_videos))
                     plan = [shard_range(vb.n_videos, i, n) for i in range(n)]
-                cap = max(vb.offsets[hi] - vb.offsets[lo] for lo, hi in plan)     # frames of the largest block
+                cap = max((vb.offsets[hi] - vb.offsets[lo] for lo, hi in plan), default=0)     # frames of the largest block
                 for i, (lo, hi) in enumerate(plan):
                     yield vb, lo, hi, i == len(plan) - 1, cap
 
         it = jobs()
         staged, done = deque(), []
+        n_blocks = [0]
         # device staging ring: block j lives in slot j % ring_slots, and its copy waits for the block that used the slot
         # before (done[j - ring_slots]) — no allocator traffic and no cross-stream frees inside the stream
         ring_slots = prefetch + 2
@@ -205,7 +209,11 @@ class TagScorer:
             if job is None:
                 return
             vb, lo, hi, last, cap = job
-            j = len(done) + len(staged)                       # index of this block in the stream
+            if vb.n_videos == 0:
+                staged.append((vb, 0, 0, True, None, None))
+                return
+            j = n_blocks[0]                                   # index of this block in the stream
+            n_blocks[0] += 1
             if j - prefetch - 2 >= 0:
                 cs.wait_event(done[j - prefetch - 2])         # bound the device copies that are alive
             with torch.cuda.stream(cs):
@@ -240,6 +248,14 @@ class TagScorer:
         pending, out, flags = None, None, None
         while staged:
             vb, lo, hi, last, piece, ev = staged.popleft()
+            if piece is None:                                 # empty batch
+                stage()
+                e = torch.cuda.Event()
+                e.record(main)
+                if pending is not None:
+                    yield finish(pending)
+                pending = (e, torch.empty(2, 0, dtype=torch.float32), None)
+                continue
             main.wait_event(ev)
             if lo == 0:
                 out = torch.empty(2, vb.n_videos, device=dev, dtype=torch.float32)

@@ -213,28 +213,7 @@ def build_train_centroids_subset(model, small_loader: Iterable, label_dict: dict
     return centroids, counts
 
 
-class TCL(torch.nn.Module):
-    """Forward of reference losses.py:6-34 in one pass over the similarity matrix (N1)."""
-
-    def __init__(self, temperature=0.1, k1=5000.0, k2=1.0):
-        super().__init__()
-        self.temperature, self.k1, self.k2 = float(temperature), float(k1), float(k2)
-
-    def loss_rows(self, projections: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        lib = _lib.load()
-        dev = _cuda_device(projections)
-        h = util_handle(dev)
-        z = projections.detach().to(dev, dtype=torch.float32).contiguous()
-        y = targets.to(dev, dtype=torch.int32).contiguous()
-        out = torch.empty(z.shape[0], device=dev, dtype=torch.float32)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
-            _lib.check(h, lib.tag_tcl_forward(h, z.data_ptr(), y.data_ptr(), z.shape[0], self.temperature, self.k1, self.k2,
-                                              out.data_ptr(), stream), "tag_tcl_forward")
-        return out
-
-    def forward(self, projections, targets):
-        return self.loss_rows(projections, targets).mean()
+from .losses import TCL  # noqa: E402,F401  (losses.py:6-34; kept importable from here)
 
 
 def write_video_scores(path: str, ac: Dict[str, float], tc: Dict[str, float]) -> Dict[str, dict]:
