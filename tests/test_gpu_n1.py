@@ -46,7 +46,7 @@ def test_supcon_hard_negatives_b4096():
     ref = O.supcon_hard_rows(a.double(), p.double(), n.double())
     loss = tb.SupConWithHardNegatives()
     rows = loss.loss_rows(a.to(DEV), p.to(DEV), n.to(DEV)).cpu().double()
-    assert ((rows - ref).abs() / ref.abs().clamp_min(1e-3)).max().item() < 2e-5
+    assert bool(((rows - ref).abs() <= 2e-6 + 2e-5 * ref.abs()).all())      # fp32 logits / 0.07: ~1e-6 absolute
     assert abs(float(loss(a.to(DEV), p.to(DEV), n.to(DEV))) - float(ref.mean())) < 1e-5 * float(ref.mean())
     # the training use: anchor == positive (train.py:519-521)
     ref2 = O.supcon_hard_rows(a, a, n)

@@ -278,18 +278,18 @@ def test_fused_pipeline_tc_scores():
     assert int(scorer.last_flags.item()) == 0
 
 
-def test_gemm_tc_halo_mode_in_subprocess():
-    """The experimental halo-tile conv path (one activation load per 64-channel chunk, taps as shifted descriptor views,
-    (t, window)-ordered accumulator rows) exists only in the EXPERIMENTS build of the library (libtag_b200_exp.so,
-    -DTAG_EXPERIMENTS; the product library reads no environment variable). It must give the same results as the default path:
-    re-run the conv GEMM and fused-GroupNorm cases of this file in a child process against that build with TAG_TC_HALO=2."""
+def test_gemm_tc_shifted_load_mode_in_subprocess():
+    """The conv GEMM's default activation path is the halo tile (one load per 64-channel chunk, taps as shifted descriptor
+    views, (t, window)-ordered accumulator rows). The plain path — five shifted TMA loads per chunk, row-major tiles — lives on
+    in the EXPERIMENTS build of the library (libtag_b200_exp.so, TAG_TC_HALO=0; the product library reads no environment
+    variable) and must pass the same conv / fused-GroupNorm cases of this file against the float64 reference."""
     import os, subprocess, sys
     if os.environ.get("TAG_TC_HALO"):
-        pytest.skip("already inside the halo-mode child")
+        pytest.skip("already inside the child")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if not os.path.exists(os.path.join(root, "video-gen-evals_b200", "libtag_b200_exp.so")):
         pytest.skip("experiments build not present")
-    env = dict(os.environ, TAG_TC_HALO="2")
+    env = dict(os.environ, TAG_TC_HALO="0")
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_exp.py"), "-m", "pytest", os.path.abspath(__file__), "-m", "gpu",
                         "-q", "-x", "-k", "(test_gemm_tc and _t5d) or fused_groupnorm"], env=env, capture_output=True, text=True,
                        timeout=600, cwd=root)

@@ -198,3 +198,54 @@ def test_centroid_allreduce_algebra_world2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_npz_ingest_reads_the_reference_layouts(tmp_path):
+    """N3: .npz (zlib-compressed, as extract_mesh.py:35 writes them, and stored) + keypoints.npy -> packed arrays, both on-disk
+    layouts, ragged lengths, float64 members, a keypoint file one frame short; names -> classes as eval.py:55-74."""
+    import importlib
+    RR = importlib.import_module("oracle.ref_runner")
+    vb = synth.make_videos(7, [64, 40, 33, 64, 7, 20, 64], seed=21, appearance=True)
+    vb.names = ["Hunyuan_PushUps_01_aa.npz", "wan21_Soccerjuggling_02_bb.npz", "Opensora_768_HulaHoop_03_cc.npz", "x_TennisSwing_1.npz",
+                "cog_WallPushups_9.npz", "Runway_Shotput_5.npz", "clip_Mystery_7.npz"]
+    want_cls = ["PushUps", "SoccerJuggling", "HulaHoop", "TennisSwing", "WallPushups", "Shotput", "Mystery"]
+    g = tmp_path / "gen"
+    RR.write_set(vb, str(g / "meshes"), str(g / "generated_kps"), generated=True, clip_dir=str(g / "clip"), dino_dir=str(g / "dino"))
+    # re-write two files the way the extraction tools do: compressed, and one with float64 members; one short keypoint file
+    d = vb.video(1)
+    np.savez_compressed(g / "meshes" / vb.names[1], pose=d["pose"].numpy(), betas=d["betas"].numpy(),
+                        global_orient=d["global_orient"].numpy(), vit=d["vit"].numpy())
+    d = vb.video(2)
+    np.savez_compressed(g / "meshes" / vb.names[2], pose=d["pose"].numpy().astype(np.float64), betas=d["betas"].numpy(),
+                        global_orient=d["global_orient"].numpy(), vit=d["vit"].numpy().astype(np.float64))
+    np.save(g / "generated_kps" / "x_TennisSwing_1" / "keypoints.npy", vb.video(3)["keypoints"].numpy()[:-1])
+    ing = tb.NpzIngest(str(g / "meshes"), str(g / "generated_kps"), generated=True, clip_dir=str(g / "clip"), dino_dir=str(g / "dino"), threads=3)
+    items = ing.scan()
+    order = sorted(range(7), key=lambda i: vb.names[i])
+    assert [it.name for it in items] == [vb.names[i] for i in order]
+    assert [it.cls for it in items] == [want_cls[i] for i in order]
+    assert [it.length for it in items] == [vb.length(i) for i in order]
+    got = ing.load(items, pin=False)
+    ref = vb.select(order)
+    for name in ("pose", "gori", "betas", "vit", "clip", "dino"):
+        assert torch.equal(getattr(got, name), getattr(ref, name)), name
+    kp_ref = ref.kp.clone()
+    j = order.index(3)
+    kp_ref[ref.offsets[j + 1] - 1] = kp_ref[ref.offsets[j + 1] - 2]        # short keypoint file: last frame repeated
+    assert torch.equal(got.kp, kp_ref)
+    assert got.offsets == ref.offsets and got.cls_idx[order.index(6)] == -1
+    assert [b.n_videos for b in ing.batches(items, videos_per_batch=3)] == [3, 3, 1]
+    # real layout (<Class>/<name>.npz), class filter
+    r = tmp_path / "real"
+    rv = synth.make_videos(6, 24, seed=22)
+    RR.write_set(rv, str(r / "meshes"), str(r / "kp"), generated=False)
+    ing2 = tb.NpzIngest(str(r / "meshes"), str(r / "kp"), generated=False, filter_classes=tb.ACTION_CLASSES[:4])
+    it2 = ing2.scan()
+    assert sorted(i.cls for i in it2) == sorted(rv.cls_name(v) for v in range(6) if rv.cls_name(v) in tb.ACTION_CLASSES[:4])
+    b2 = ing2.load(it2, pin=False)
+    k = [rv.names.index(i.name) for i in it2]
+    assert torch.equal(b2.vit, rv.select(k).vit) and torch.equal(b2.kp, rv.select(k).kp)
+    # a missing keypoint file is the reference's FileNotFoundError (utils.py:416-417)
+    os.remove(r / "kp" / it2[0].cls / os.path.splitext(it2[0].name)[0] / "keypoints.npy")
+    with pytest.raises(FileNotFoundError):
+        ing2.scan()

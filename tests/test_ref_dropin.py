@@ -204,4 +204,23 @@ def test_reporting_parity_process_scores_and_spearman(bench300, tmp_path):
         r_ours, _, m1 = ref.eval.compute_spearman_correlation({k: v[key] for k, v in ours.items()}, RR.HUMAN_SCORES, key)
         r_ref, _, m2 = ref.eval.compute_spearman_correlation({k: v[key] for k, v in theirs.items()}, RR.HUMAN_SCORES, key)
         print(f"Spearman vs human {key}: ours {r_ours:.4f} reference {r_ref:.4f} ({len(m1)} matched)")
-        assert len(m1) == len(m2) == b.n and abs(r_ours - r_ref) < 5e-3
+        assert len(m1) == len(m2) >= 0.7 * b.n and abs(r_ours - r_ref) < 5e-3     # eval.py:318-331 matches most, not all, names
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_score_files_from_reference_layout(bench300):
+    """N3: scoring straight from the reference's on-disk files (ingest -> pinned batches -> device ring -> scores) gives the
+    reference's per-video scores; batches smaller than the set exercise the background loader."""
+    b = bench300
+    model = b.our_model("fp16_tc")
+    scorer = tb.TagScorer(model, b.stats, 32, 8, DEV)
+    ing = tb.NpzIngest(b.gen_dir, b.gen_kp, generated=True)
+    items = ing.scan()
+    assert len(items) == b.n
+    d = scorer.score_files(ing, b.cen.to(DEV), items, videos_per_batch=128)
+    assert set(d) == set(b.ac)
+    e_ac = max(abs(d[k]["ac"] - b.ac[k]) / b.ac[k] for k in b.ac)
+    e_tc = max(abs(d[k]["tc"] - b.tc[k]) / b.tc[k] for k in b.tc)
+    print(f"score_files (from .npz/.npy): AC rel {e_ac:.2e} TC rel {e_tc:.2e} ({len(d)} videos)")
+    assert e_ac < 1e-3 and e_tc < 1e-3

@@ -18,7 +18,25 @@ Wt = (torch.randn(N, 5 * K, device=DEV, generator=g) / math.sqrt(5 * K)).half()
 R16 = torch.randn(M, N, device=DEV, generator=g).half()
 C16 = torch.empty(M, N, device=DEV, dtype=torch.float16)
 gam, bet = torch.ones(N, device=DEV), torch.zeros(N, device=DEV)
-print("env: HALO=%s PAIR=%s DEBUG=%s" % (os.environ.get("TAG_TC_HALO", "0"), os.environ.get("TAG_TC_PAIR", "1"), os.environ.get("TAG_TC_DEBUG", "0")))
+print("env: HALO=%s ASTAGES=%s PAIR=%s DEBUG=%s" % (os.environ.get("TAG_TC_HALO", "0"), os.environ.get("TAG_TC_HALO_ASTAGES", "3"), os.environ.get("TAG_TC_PAIR", "1"), os.environ.get("TAG_TC_DEBUG", "0")))
+if os.environ.get("TAG_CUBLAS", "0") != "0":
+    # same-shape library comparator (cuBLAS through torch.matmul, fp16 operands, fp32 accumulate): the conv as an im2col GEMM
+    # (K = 1280; the im2col matrix is NOT built by our kernel and is not charged here either) and the K = 4096 plain GEMM
+    for Kc in (1280, 4096):
+        Ac = torch.randn(M, Kc, device=DEV, generator=g).half()
+        Bc = torch.randn(Kc, N, device=DEV, generator=g).half()
+        for _ in range(3):
+            torch.matmul(Ac, Bc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            torch.matmul(Ac, Bc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"cuBLAS fp16 [{M} x {Kc}] @ [{Kc} x {N}]: {ms * 1e3:8.1f} us  {2.0 * M * N * Kc / ms / 1e9:8.1f} TFLOP/s", flush=True)
+        del Ac, Bc
 for dil in (1, 2, 4, 8):
     for name, res, gn in (("conv1 gelu", None, False), ("conv2+GN", R16, True)):
         def run():

@@ -23,5 +23,6 @@ from .scoring import (extract_window_features, compute_temporal_coherence_scores
 from .losses import TCL, SupConWithHardNegatives, hard_negative_step
 from .augment import partial_shuffle_within_window, reverse_sequence, get_static_window, gather_frames
 from .pipeline import TagScorer, block_plan, shard_range, window_table
+from .ingest import NpzIngest, FileItem, class_from_filename
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -10,16 +10,16 @@
 // coordinate is shifted by (j-2)*dil — TMA's out-of-bounds zero fill IS the conv's zero padding — all
 // accumulating into one TMEM tile.
 //
-// Halo mode (TAG_TC_HALO=1|2, off by default): the five shifted loads re-read every activation row five times from
+// Halo mode (the default conv path since round 2): five shifted loads would re-read every activation row five times from
 // L2 (~1 GB of the ~2 GB L2->SM traffic of a conv launch). In halo mode the producer loads each 64-channel chunk ONCE
 // as a box (channel, window, t) = (64, NW, T' + 4*dil) starting at t = -2*dil: rows land in shared memory ordered
 // (t, window) — row = (t + 2*dil) * NW + w — with TMA's zero fill supplying the conv padding rows, and tap j is the
 // same tile read through a descriptor whose start address is advanced by j*dil*NW rows. The accumulator rows are then
 // (t, window)-ordered too; the epilogue maps them back to [window][t] rows when it addresses global memory.
-// Measured on B200 (same box, A/B): bit-identical results, 5x less activation traffic from L2, but 2-3 % SLOWER
-// (conv share of a bench step 212-215 ms vs 206-210 ms): the kernel is bound by the board power cap (SM clock
-// 1.55-1.75 GHz under sw_power_cap), not by L2->SM bandwidth, and the deeper {A,B} ring hides latency better than
-// 2 A + 6 B stages. Kept selectable because it is the right design if the L2 path ever becomes the limiter.
+// Measured on B200 (same box, A/B, round 2: profiles/r2_halo_microbench.log): bit-identical results, 5x less activation
+// traffic from L2, conv1 + GELU 225-231 us vs 237-262 us per 400,000-row launch (1.14-1.17 vs 1.00-1.10 PFLOP/s; the library's
+// im2col GEMM of the same shape, cuBLAS fp16 [400000 x 1280] x [1280 x 256], runs at 1.09 PFLOP/s), conv2 + GroupNorm 261-269 vs
+// 277-303 us, 2.5-3 % on the whole scoring step. (Round 1 measured it 2-3 % slower on that day's boxes and kept it off.)
 //
 // CTA = 576 threads (18 warps), one CTA per SM, persistent over output tiles; by default two CTAs form a cluster and one
 // cta_group::2 MMA (256x256 tile per pair, 128 rows per CTA):
@@ -55,10 +55,12 @@ template <bool PAIR> struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
 };
-// barrier slots (8 B each): full_b[8], empty_b[8], full_a[2], empty_a[2], tmem_full[2], tmem_empty[2]. Without halo
+// barrier slots (8 B each): full_b[8], empty_b[8], full_a[4], empty_a[4], tmem_full[2], tmem_empty[2]. Without halo
 // mode a stage holds {A, B} together and only the *_b barriers are used.
 constexpr int MAX_STAGES = 8;
-constexpr int MAX_BARS = 2 * MAX_STAGES + 4 + 4;
+constexpr int MAX_A_STAGES = 4;               // halo mode: activation chunk stages
+constexpr int MAX_BARS = 2 * MAX_STAGES + 2 * MAX_A_STAGES + 4;
+constexpr int BAR_BYTES = 512;                // barriers, TMEM base word, GroupNorm pair-exchange slots
 constexpr int EPI_WARPS = 16;                 // 4 per TMEM lane quarter, 64 accumulator columns each
 constexpr int EPI_COLS = BLOCK_N / (EPI_WARPS / 4);   // 64
 constexpr int CW = 16;                        // columns per tcgen05.ld chunk
@@ -69,7 +71,7 @@ constexpr int RING_BYTES = 5 * (A_BYTES + (BLOCK_N / 2) * BLOCK_K * 2);      // 
 constexpr int STG_WARP_BYTES = 32 * 64;            // per-epilogue-warp staging tile: 32 rows x 64 B, XOR-swizzled
 constexpr int STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
 constexpr int GN_AFFINE_BYTES = 2 * BLOCK_N * 4;           // gamma[256] || beta[256]
-constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GN_RED_BYTES + GN_AFFINE_BYTES + STG_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + BAR_BYTES + GN_RED_BYTES + GN_AFFINE_BYTES + STG_BYTES;
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address -> the pair's leader CTA
 
 // tcgen05 instruction descriptor (Cfg::IDESC), kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major A and B,
@@ -107,7 +109,8 @@ struct TcParams {
   int dbg;                 // bottleneck experiments (TAG_TC_DEBUG): 1 no epilogue stores, 2 no weight loads, 4 no activation loads
   // halo mode (conv): A chunk loaded once per 64 channels with its time halo, taps = shifted descriptor views
   int halo;                // 0 off, 1 on, 2 on with the descriptor base-offset field set for unaligned tap shifts (experiment)
-  int a_stage_bytes;       // bytes of one staged A chunk (multiple of 1024); two A stages
+  int a_stage_bytes;       // bytes of one staged A chunk (multiple of 1024)
+  int a_stages;            // staged A chunks in flight (2..4)
   int a_box_bytes;         // bytes the TMA box delivers (zero-filled rows included)
   int b_stages;            // weight-tile stages behind the two A stages
   int g_L, g_wpv, g_stride;   // mode 3: frames per clip, windows per clip, window stride (frames)
@@ -402,16 +405,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto fulla_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
-  auto emptya_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 4 + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 6 + a); };
+  auto emptya_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + MAX_A_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 * MAX_A_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * MAX_BARS;
   // GroupNorm pair exchange (T == 256): two mbarriers and two (sum, sumsq) slots, alternating by tile parity
-  auto xbar = [&](int i) { return bar_base + 208u + 8u * i; };
-  auto xslot = [&](int i) { return bar_base + 224u + 8u * i; };
+  auto xbar = [&](int i) { return bar_base + 8u * (MAX_BARS + 2) + 8u * i; };
+  auto xslot = [&](int i) { return bar_base + 8u * (MAX_BARS + 4) + 8u * i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* s_gb = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256 + GN_RED_BYTES);
+  float* s_gb = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES + GN_RED_BYTES);
   if constexpr (GN) {
     for (int i = threadIdx.x; i < BLOCK_N; i += THREADS) { s_gb[i] = __ldg(p.gn_gamma + i); s_gb[BLOCK_N + i] = __ldg(p.gn_beta + i); }
   }
@@ -421,7 +424,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 1); }
+    for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(fulla_bar(s), 1); mbar_init(emptya_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * (PAIR ? 2 : 1)); }
     for (int a = 0; a < 2; ++a) mbar_init(xbar(a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -457,7 +460,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const bool ld_a = !(p.dbg & 4), ld_b = !(p.dbg & 2);
       if (p.halo) {
         const int pad = (p.taps / 2) * p.dil;
-        const uint32_t b_ring = smem_base + 2u * (uint32_t)p.a_stage_bytes;
+        const uint32_t b_ring = smem_base + (uint32_t)(p.a_stages * p.a_stage_bytes);
         for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
           const int64_t m_tile = m_tile_of(tile);
           const int n_tile = (int)(tile % p.n_tiles);
@@ -474,7 +477,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               if (ld_a) { mbar_arrive_expect_tx(fulla_bar(sa_i), (uint32_t)p.a_box_bytes); tma_load_3d(da, &map_a, fulla_bar(sa_i), kc * BLOCK_K, cw, ct); }
               else mbar_arrive(fulla_bar(sa_i));
             }
-            if (++sa_i == 2) { sa_i = 0; pa ^= 1u; }
+            if (++sa_i == p.a_stages) { sa_i = 0; pa ^= 1u; }
             for (int j = 0; j < p.taps; ++j) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t db = b_ring + (uint32_t)(stage * Cfg<PAIR>::B_BYTES);
@@ -552,7 +555,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         if (p.halo) {
-          const uint32_t b_ring = smem_base + 2u * (uint32_t)p.a_stage_bytes;
+          const uint32_t b_ring = smem_base + (uint32_t)(p.a_stages * p.a_stage_bytes);
           for (int kc = 0; kc < p.kb_per_tap; ++kc) {
             mbar_wait(fulla_bar(sa_i), pa);                     // this 64-channel chunk (with its time halo) has landed
             tc_fence_after();
@@ -572,7 +575,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               if (++stage == p.b_stages) { stage = 0; phase ^= 1u; }
             }
             if constexpr (PAIR) umma_commit_pair(emptya_bar(sa_i)); else umma_commit(emptya_bar(sa_i));
-            if (++sa_i == 2) { sa_i = 0; pa ^= 1u; }
+            if (++sa_i == p.a_stages) { sa_i = 0; pa ^= 1u; }
           }
         } else
         for (int kb = 0; kb < n_kb; ++kb) {
@@ -600,7 +603,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int part = (warp - 2) >> 2;          // which 64 accumulator columns
     constexpr int NCH = EPI_COLS / CW;         // 4 chunks of 16 columns
-    const uint32_t stg = bar_base + 256u + GN_RED_BYTES + GN_AFFINE_BYTES + (uint32_t)((warp - 2) * STG_WARP_BYTES);
+    const uint32_t stg = bar_base + (uint32_t)BAR_BYTES + GN_RED_BYTES + GN_AFFINE_BYTES + (uint32_t)((warp - 2) * STG_WARP_BYTES);
     const bool out32 = p.C32 != nullptr;
     int64_t it = 0;
     for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
@@ -652,7 +655,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
         // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 4 column parts
-        const uint32_t red = bar_base + 256u + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
+        const uint32_t red = bar_base + (uint32_t)BAR_BYTES + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
         float S1 = 0.f, S2 = 0.f;
         if (p.halo) {
           // (t, window)-ordered tile: lane l of EVERY epilogue warp holds rows of window l & (NW-1)
@@ -760,7 +763,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         }
         tmem_st_wait();
         // ---- row statistics across the 4 column parts of this lane quarter
-        const uint32_t red = bar_base + 256u + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
+        const uint32_t red = bar_base + (uint32_t)BAR_BYTES + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
         float S1 = 0.f, S2 = 0.f;
@@ -965,9 +968,14 @@ struct TcContext {
   int num_sms = 148;
   bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
   int dbg = 0;            // TAG_TC_DEBUG bottleneck experiments (results are wrong when set)
-  int halo = 0;           // TAG_TC_HALO: 0 five shifted loads per chunk (default), 1 halo tiles when the tap shift is 8-row
-                          // aligned, 2 halo tiles for every dilation (unaligned descriptor start address: correct on B200),
-                          // 3 = 2 with the descriptor base-offset field set (WRONG results on B200; kept as a probe)
+  int halo_a_stages = 2;  // activation chunks in flight in halo mode (2..4; 3 and 4 measured no faster, and slower at dilation 8
+                          // where they leave only 4 weight stages — profiles/r2_halo_microbench.log)
+  int halo = 2;           // conv activation loads: 2 (default) = halo tiles for every dilation — one load per 64-channel chunk, the five
+                          // taps are descriptor views shifted by j*dil*NW rows (a start row that is not a multiple of 8 is read
+                          // correctly by tcgen05.mma on B200 with base-offset 0; held bit-identical to mode 0 by the tests);
+                          // 0 = five shifted TMA loads per chunk, 1 = halo only when the tap shift is 8-row aligned,
+                          // 3 = 2 with the descriptor base-offset field set (WRONG on B200; probe). Only the experiments
+                          // build can change it (TAG_TC_HALO).
 };
 
 TcContext* tc_context_create(int device, char* err, int errlen) {
@@ -998,6 +1006,8 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   if (env != nullptr) c->dbg = atoi(env);
   env = getenv("TAG_TC_HALO");
   if (env != nullptr) c->halo = atoi(env);
+  env = getenv("TAG_TC_HALO_ASTAGES");
+  if (env != nullptr) { c->halo_a_stages = atoi(env); if (c->halo_a_stages < 2) c->halo_a_stages = 2; if (c->halo_a_stages > MAX_A_STAGES) c->halo_a_stages = MAX_A_STAGES; }
 #endif
   if (e != cudaSuccess) {
     snprintf(err, errlen, "cudaFuncSetAttribute(k_gemm_tc, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e));
@@ -1076,14 +1086,16 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
       const int pad = (g.taps / 2) * g.dil;
       const int rows = nw * (tp + 2 * pad);
       const int a_stage = (rows * 128 + 1023) & ~1023;
-      const int b_stages = (RING_BYTES - 2 * a_stage) / b_bytes;
+      int a_stages = ctx->halo_a_stages;
+      while (a_stages > 2 && (RING_BYTES - a_stages * a_stage) / b_bytes < 3) --a_stages;
+      const int b_stages = (RING_BYTES - a_stages * a_stage) / b_bytes;
       const bool aligned = (g.dil * nw) % 8 == 0;
       if (nw <= 32 && tp + 2 * pad <= 256 && g.dil >= 1 && b_stages >= 2 && (aligned || ctx->halo >= 2)) {
         int lw = 0, lt = 0;
         while ((1 << lw) < nw) ++lw;
         while ((1 << lt) < tp) ++lt;
         p.halo = (!aligned && ctx->halo == 3) ? 2 : 1;
-        p.a_stage_bytes = a_stage; p.a_box_bytes = rows * 128;
+        p.a_stage_bytes = a_stage; p.a_box_bytes = rows * 128; p.a_stages = a_stages;
         p.b_stages = b_stages < MAX_STAGES ? b_stages : MAX_STAGES;
         p.tap_rows = g.dil * nw;
         p.lw = nw > 1 ? lw : 0; p.lt = lt;

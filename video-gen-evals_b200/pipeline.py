@@ -310,6 +310,23 @@ class TagScorer:
         results (`score_stream` over a single batch). Returns CPU tensors (ac [V], tc [V])."""
         return next(iter(self.score_stream([vb_host], centroids, pieces=pieces, prefetch=pieces)))
 
+    def score_files(self, ingest, centroids: torch.Tensor, items=None, videos_per_batch: int = 5000) -> Dict[str, Dict[str, float]]:
+        """eval.py:394-451 from FILES: `ingest` (ingest.NpzIngest over the reference's on-disk layout) parses `.npz` /
+        `keypoints.npy` into pinned host batches on background threads, `score_stream` moves them through the device staging
+        ring and scores them; returns {video_id: {"ac","tc"}} (what eval.py writes to video_scores.json)."""
+        out: Dict[str, Dict[str, float]] = {}
+        held = []
+
+        def feed():
+            for vb in ingest.batches(items, videos_per_batch):
+                held.append(vb)
+                yield vb
+
+        for i, (ac, tc) in enumerate(self.score_stream(feed(), centroids)):
+            out.update(self.scores_dict(held[i], ac, tc))
+            held[i] = None
+        return out
+
     def scores_dict(self, vb: VideoBatch, ac: torch.Tensor, tc: torch.Tensor) -> Dict[str, Dict[str, float]]:
         """{video_id: {"ac","tc"}} as eval.py:439-447 (a key is absent when the reference would skip it)."""
         ac, tc = ac.cpu().tolist(), tc.cpu().tolist()
