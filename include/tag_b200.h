@@ -209,6 +209,13 @@ int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, 
                       void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta,
                       const float* ln_gamma, const float* ln_beta, void* stream);
 
+/* the fused tail of one transformer layer (model.py:145, post-norm): x32 <- LN2(x1 + relu(x1 W1^T + b1) W2^T + b2) with
+ * x1 = LN1(x32 + att16 Wo^T + bo), in place, plus the fp16 copy x16; M > 128 rows, ffn_dim a multiple of 256; weights fp16
+ * [out, in] row-major. This is the kernel tag_encode* runs once per layer in tensor-core mode. */
+int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x16, int64_t M, int32_t ffn_dim, const void* Wo16,
+                          const void* W1_16, const void* W2_16, const float* bo, const float* b1, const float* b2,
+                          const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,3 +359,45 @@ def test_gemm_tc_fused_layernorm(M, K):
     scale = max(1.0, ref.abs().max().item())
     assert (X.double() - ref).abs().max().item() < 2e-4 * scale, _diag(X, ref, "LN fp32")
     assert (X16.double() - ref).abs().max().item() < 2e-3 * scale, _diag(X16, ref, "LN fp16")
+
+
+@pytest.mark.parametrize("M,F", [(257, 1024), (330, 1024), (128 * 9 + 5, 1024), (4096, 1024), (20000, 1024), (700, 512)])
+def test_tlayer_tail_fused(M, F):
+    """The fused transformer-layer tail (tlayer_tc.cu; model.py:145 post-norm layer after attention):
+    x1 = LN1(x + att Wo^T + bo); x = LN2(x1 + relu(x1 W1^T + b1) W2^T + b2), against float64 with the kernel's two operand
+    roundings (x1 and relu(h) enter the next GEMM as fp16) — odd tile counts, a partial last tile, many tiles per CTA pair."""
+    lib = _lib.load()
+    h = tb.scoring.util_handle(DEV)
+    D = 256
+    g = torch.Generator(device=DEV).manual_seed(M + F)
+    att = torch.randn(M, D, device=DEV, generator=g).half()
+    X = torch.randn(M, D, device=DEV, generator=g)
+    Wo = (torch.randn(D, D, device=DEV, generator=g) / math.sqrt(D)).half()
+    W1 = (torch.randn(F, D, device=DEV, generator=g) / math.sqrt(D)).half()
+    W2 = (torch.randn(D, F, device=DEV, generator=g) / math.sqrt(F)).half()
+    bo, b1, b2 = (0.1 * torch.randn(n, device=DEV, generator=g) for n in (D, F, D))
+    g1, be1, g2, be2 = (1.0 + 0.1 * torch.randn(D, device=DEV, generator=g), 0.05 * torch.randn(D, device=DEV, generator=g),
+                        1.0 + 0.1 * torch.randn(D, device=DEV, generator=g), 0.05 * torch.randn(D, device=DEV, generator=g))
+
+    def ln(v, gam, bet):
+        return (v - v.mean(1, keepdim=True)) / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-5) * gam.double() + bet.double()
+
+    x1 = ln(X.double() + att.double() @ Wo.double().T + bo.double(), g1, be1)
+    hid = torch.relu(x1.float().half().double() @ W1.double().T + b1.double())
+    ref = ln(x1 + hid.float().half().double() @ W2.double().T + b2.double(), g2, be2)
+    Xio = X.clone()
+    X16 = torch.full((M, D), float("nan"), device=DEV, dtype=torch.float16)
+    rc = lib.tag_debug_tlayer_tail(h, att.data_ptr(), Xio.data_ptr(), X16.data_ptr(), M, F, Wo.data_ptr(), W1.data_ptr(), W2.data_ptr(),
+                                   bo.data_ptr(), b1.data_ptr(), b2.data_ptr(), g1.data_ptr(), be1.data_ptr(), g2.data_ptr(),
+                                   be2.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(h, rc, "tag_debug_tlayer_tail")
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    e32 = (Xio.double() - ref).abs().max().item()
+    print(f"tlayer_tail M={M} F={F}: fp32 out max err {e32:.2e} (scale {scale:.2f})")
+    assert e32 < 1e-3 * scale, _diag(Xio, ref, "tail fp32")
+    assert (X16.double() - ref).abs().max().item() < 3e-3 * scale, _diag(X16, ref, "tail fp16")
+    # unsupported shapes are refused up front, not mid-kernel
+    assert lib.tag_debug_tlayer_tail(h, att.data_ptr(), Xio.data_ptr(), X16.data_ptr(), 100, F, Wo.data_ptr(), W1.data_ptr(), W2.data_ptr(),
+                                     bo.data_ptr(), b1.data_ptr(), b2.data_ptr(), g1.data_ptr(), be1.data_ptr(), g2.data_ptr(),
+                                     be2.data_ptr(), torch.cuda.current_stream().cuda_stream) != 0

@@ -259,6 +259,126 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h(const MergeParams p) {
   Row8<__half>::store(reinterpret_cast<__half*>(p.mix) + r * kD + lane * 8, mix);
 }
 
+// Two rows per warp (round 2): the kernel above is instruction-issue bound (ncu: 737 warp instructions per row, 61 % of the
+// issue slots, 0.38 of the HBM peak) and a third of those are warp-wide shuffle reductions and per-row scalar work that a
+// 32-lane row pays once per ROW. Here a row is 16 lanes x 16 columns (two 16-byte loads per lane and modality: columns
+// [8s, 8s+8) and [128+8s, 128+8s+8) of half-warp lane s, so a half-warp still reads two contiguous 256-byte runs), the
+// reductions are 4 xor-steps that never leave the half-warp, and every shuffle / softmax instruction serves two rows.
+// gamma / beta / gamma*qk come from shared memory (loaded once per CTA). No separate motion tensors (the tensor-core path
+// always feeds s = state + motion from the fused projection GEMM).
+template <int MM>
+__global__ void __launch_bounds__(256) k_merge_fusion_h2(const MergeParams p) {
+  __shared__ __align__(16) float s_g[kD], s_b[kD], s_gq[kD];
+  __shared__ float s_bq;
+  for (int i = threadIdx.x; i < kD; i += blockDim.x) {
+    const float g = __ldg(p.kv_gamma + i), b = __ldg(p.kv_beta + i), q = __ldg(p.qk + i);
+    s_g[i] = g; s_b[i] = b; s_gq[i] = g * q;
+  }
+  if (threadIdx.x < 32) {
+    float bq = 0.f;
+    for (int i = threadIdx.x; i < kD; i += 32) bq = fmaf(__ldg(p.kv_beta + i), __ldg(p.qk + i), bq);
+    bq = warp_sum(bq);
+    if (threadIdx.x == 0) s_bq = bq;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const int64_t r = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 5) * 2 + (lane >> 4);
+  const bool live = r < p.R;
+  const int c0 = sub * 8, c1 = 128 + sub * 8;
+  float d[MM][16], s1[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    uint4 ua = make_uint4(0u, 0u, 0u, 0u), ub = ua;
+    if (live && m < p.M) {
+      const __half* src = reinterpret_cast<const __half*>(p.ps[m]) + r * kD;
+      ua = __ldg(reinterpret_cast<const uint4*>(src + c0));
+      ub = __ldg(reinterpret_cast<const uint4*>(src + c1));
+    }
+    const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+    const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+    s1[m] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(ha[i]), b = __half22float2(hb[i]);
+      d[m][2 * i] = a.x; d[m][2 * i + 1] = a.y; d[m][8 + 2 * i] = b.x; d[m][8 + 2 * i + 1] = b.y;
+      s1[m] += (a.x + a.y) + (b.x + b.y);
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+    for (int m = 0; m < MM; ++m) s1[m] += __shfl_xor_sync(FULL_MASK, s1[m], o);
+  }
+  float s2[MM], sq[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) { s2[m] = 0.f; sq[m] = 0.f; }
+#pragma unroll
+  for (int hblk = 0; hblk < 2; ++hblk) {
+    const float4 q0 = *reinterpret_cast<const float4*>(s_gq + (hblk ? c1 : c0));
+    const float4 q1 = *reinterpret_cast<const float4*>(s_gq + (hblk ? c1 : c0) + 4);
+    const float gq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int m = 0; m < MM; ++m) {
+      const float mean = s1[m] * (1.0f / kD);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float x = d[m][hblk * 8 + k] - mean;
+        d[m][hblk * 8 + k] = x;
+        s2[m] = fmaf(x, x, s2[m]);
+        sq[m] = fmaf(x, gq[k], sq[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+    for (int m = 0; m < MM; ++m) { s2[m] += __shfl_xor_sync(FULL_MASK, s2[m], o); sq[m] += __shfl_xor_sync(FULL_MASK, sq[m], o); }
+  }
+  const float bq = s_bq;
+  float logit[MM], sc[MM];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const float var = s2[m] * (1.0f / kD);
+    const float rstd1 = rsqrtf(var + kLnEps);
+    const float var_u = var * rstd1 * rstd1;
+    sc[m] = rstd1 * rsqrtf(var_u + kLnEps);
+    logit[m] = -CUDART_INF_F;
+    if (m < p.M) {
+      logit[m] = fmaf(sc[m], sq[m], bq) * p.inv_tau[m] + p.lbias[m];
+      mx = fmaxf(mx, logit[m]);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int m = 0; m < MM; ++m) { logit[m] = (m < p.M) ? __expf(logit[m] - mx) : 0.f; den += logit[m]; }
+  const float inv_den = __fdividef(1.0f, den);
+  float wgt[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    const float a = logit[m] * inv_den;
+    wgt[m] = a * sc[m];
+    if (p.attn != nullptr && sub == 0 && live && m < p.M) p.attn[r * p.M + m] = a;
+  }
+#pragma unroll
+  for (int hblk = 0; hblk < 2; ++hblk) {
+    const int c = hblk ? c1 : c0;
+    float mix[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int m = 0; m < MM; ++m) a = fmaf(wgt[m], d[m][hblk * 8 + k], a);
+      mix[k] = a;
+    }
+    const float4 g0 = *reinterpret_cast<const float4*>(s_g + c), g1 = *reinterpret_cast<const float4*>(s_g + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(s_b + c), b1 = *reinterpret_cast<const float4*>(s_b + c + 4);
+    mix[0] = fmaf(mix[0], g0.x, b0.x); mix[1] = fmaf(mix[1], g0.y, b0.y); mix[2] = fmaf(mix[2], g0.z, b0.z); mix[3] = fmaf(mix[3], g0.w, b0.w);
+    mix[4] = fmaf(mix[4], g1.x, b1.x); mix[5] = fmaf(mix[5], g1.y, b1.y); mix[6] = fmaf(mix[6], g1.z, b1.z); mix[7] = fmaf(mix[7], g1.w, b1.w);
+    if (live) Row8<__half>::store(reinterpret_cast<__half*>(p.mix) + r * kD + c, mix);
+  }
+}
+
 // ---------------------------------------------------------------- tokens = [cls ; frames] + PE
 template <typename TA>
 __global__ void __launch_bounds__(256) k_build_tokens(const TA* __restrict__ fused, const float* __restrict__ cls,
@@ -792,6 +912,7 @@ cudaError_t launch_merge_fusion(const MergeParams& p, cudaStream_t s) {
   if constexpr (sizeof(TA) == 2) {
     bool hm = false;
     for (int m = 0; m < p.M; ++m) hm = hm || p.pm[m] != nullptr;
+    if (p.M <= 5 && !hm) { k_merge_fusion_h2<5><<<(unsigned)((p.R + 15) / 16), 256, 0, s>>>(p); return cudaGetLastError(); }
     if (p.M <= 5) { if (hm) k_merge_fusion_h<5, true><<<grid, 256, 0, s>>>(p); else k_merge_fusion_h<5, false><<<grid, 256, 0, s>>>(p); }
     else { if (hm) k_merge_fusion_h<TAG_MAX_MODALITIES, true><<<grid, 256, 0, s>>>(p); else k_merge_fusion_h<TAG_MAX_MODALITIES, false><<<grid, 256, 0, s>>>(p); }
     return cudaGetLastError();

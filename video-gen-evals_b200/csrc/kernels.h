@@ -142,3 +142,20 @@ TcContext* tc_context_create(int device, char* err, int errlen);
 void tc_context_destroy(TcContext*);
 bool tc_pair_enabled(const TcContext*);   // CTA pairs (cta_group::2) in use: fused GroupNorm then also covers T == 256
 cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char* err, int errlen);
+void* tc_encode_fn(const TcContext*);     // cuTensorMapEncodeTiled entry point
+int tc_num_sms(const TcContext*);
+
+// ------------------------------------------------------------------ fused transformer-layer tail (tlayer_tc.cu)
+// x <- LN2(x1 + relu(x1 W1^T + b1) W2^T + b2), x1 = LN1(x + att Wo^T + bo): out-proj + norm1 + FFN + norm2 of one post-norm
+// layer (model.py:145) in one tcgen05 kernel; x32 is updated in place, x16 receives its fp16 copy
+struct TlayerTail {
+  int64_t M; int ffn_dim;
+  const __half* att16;            // [M,256] attention output (fp16)
+  float* x32; __half* x16;        // [M,256] token stream (fp32, in/out) and its fp16 copy (out)
+  const __half* Wo16;             // [256,256]
+  const __half* W1_16;            // [ffn,256]
+  const __half* W2_16;            // [256,ffn]
+  const float *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+bool tlayer_tail_supported(int64_t M, int ffn_dim);
+cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t, cudaStream_t s, char* err, int errlen);

@@ -85,6 +85,7 @@ struct tag_handle {
   int32_t* zeros = nullptr;         // [max_windows] 0
   int32_t *clip_wv = nullptr, *clip_ws = nullptr;   // [max_windows] window table of one pass (fallback path)
   float* row0 = nullptr;            // [M][256]: motion stem applied to the z-scored zero difference
+  int fuse_tail = 1;                // fused transformer-layer tail (TAG_FUSE_TAIL=0 selects the three separate GEMMs in TAG_EXPERIMENTS builds)
   int frame_table = 1;              // frame-table mode of tag_encode_clips (TAG_FRAME_TABLE=0 disables it in TAG_EXPERIMENTS builds)
   float* attn_out = nullptr;        // tag_set_fusion_attn_out: [rows, M] fusion softmax of the NEXT tag_encode call (model.py:94 last_attn)
   __half *tcl_A = nullptr, *tcl_W = nullptr;   // tensor-core TCL: split-fp16 operands [Bp, 768] and the per-slice partial sums
@@ -403,6 +404,22 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
     q.C16 = QKV; q.ldc = 3 * kD;
     rc = gemm_tc_run(h, s, q, 2.0 * R2 * 3 * kD * kD); if (rc) return rc;
     { ProfScope ps(h, s, 6, (double)R2 * kD * 8); LAUNCH_TRY(h, launch_attention<__half>(QKV, ATT, W, T + 1, h->cfg.n_heads, s)); }
+    if (h->fuse_tail && tlayer_tail_supported(R2, F)) {
+      // out-proj + norm1 + FFN1 + ReLU + FFN2 + norm2 in ONE kernel (tlayer_tc.cu): the FFN hidden state, x1 and its fp16
+      // copy stay in TMEM / shared memory
+      TlayerTail t{};
+      t.M = R2; t.ffn_dim = F; t.att16 = ATT; t.x32 = h->X; t.x16 = X16; t.Wo16 = L.out_w16; t.W1_16 = L.l1_w16; t.W2_16 = L.l2_w16;
+      t.bo = L.out_b; t.b1 = L.l1_b; t.b2 = L.l2_b; t.ln1_g = L.n1_g; t.ln1_b = L.n1_b; t.ln2_g = L.n2_g; t.ln2_b = L.n2_b;
+      ProfScope ps(h, s, 2, 2.0 * R2 * kD * kD + 4.0 * R2 * F * kD);
+      h->err[0] = 0;
+      cudaError_t e = launch_tlayer_tail(tc_encode_fn(h->tc), tc_num_sms(h->tc), t, s, h->err, 512);
+      h->launches++;
+      if (e != cudaSuccess) {
+        if (h->err[0] == 0) fail(h, TAG_ERR_CUDA, "tlayer_tail launch failed: %s", cudaGetErrorString(e));
+        return TAG_ERR_CUDA;
+      }
+      continue;
+    }
     GemmTC o{};
     o.A = ATT; o.M = R2; o.lda = kD; o.W = L.out_w16; o.N = kD; o.K = kD; o.taps = 1; o.dil = 1; o.T = 1; o.bias = L.out_b;
     // out-proj + bias + residual + LayerNorm(norm1) in one kernel, in place over the fp32 token stream
@@ -755,6 +772,8 @@ int tag_finalize_weights(tag_handle* h) {
 #ifdef TAG_EXPERIMENTS
     const char* env = getenv("TAG_FRAME_TABLE");
     if (env != nullptr) h->frame_table = atoi(env);
+    env = getenv("TAG_FUSE_TAIL");
+    if (env != nullptr) h->fuse_tail = atoi(env);
 #endif
   } else {
     if ((rc = dev_alloc(h, &h->feats, R * h->D))) return rc;
@@ -1103,6 +1122,29 @@ int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, 
   g.gn_gamma = gn_gamma; g.gn_beta = gn_beta; g.ln_gamma = ln_gamma; g.ln_beta = ln_beta;
   h->err[0] = 0;
   return gemm_tc_run(h, (cudaStream_t)stream, g, 2.0 * (double)M * N * K * taps);
+}
+
+int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x16, int64_t M, int32_t ffn_dim, const void* Wo16,
+                          const void* W1_16, const void* W2_16, const float* bo, const float* b1, const float* b2, const float* ln1_g,
+                          const float* ln1_b, const float* ln2_g, const float* ln2_b, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->tc) {
+    h->tc = tc_context_create(h->cfg.device, h->err, 512);
+    if (!h->tc) return TAG_ERR_CUDA;
+  }
+  TlayerTail t{};
+  t.M = M; t.ffn_dim = ffn_dim; t.att16 = (const __half*)att16; t.x32 = x32; t.x16 = (__half*)x16; t.Wo16 = (const __half*)Wo16;
+  t.W1_16 = (const __half*)W1_16; t.W2_16 = (const __half*)W2_16; t.bo = bo; t.b1 = b1; t.b2 = b2;
+  t.ln1_g = ln1_g; t.ln1_b = ln1_b; t.ln2_g = ln2_g; t.ln2_b = ln2_b;
+  h->err[0] = 0;
+  cudaError_t e = launch_tlayer_tail(tc_encode_fn(h->tc), tc_num_sms(h->tc), t, (cudaStream_t)stream, h->err, 512);
+  h->launches++;
+  if (e != cudaSuccess) {
+    if (h->err[0] == 0) fail(h, TAG_ERR_CUDA, "tlayer_tail launch failed: %s", cudaGetErrorString(e));
+    return e == cudaErrorInvalidValue ? TAG_ERR_INVALID : TAG_ERR_CUDA;
+  }
+  return TAG_OK;
 }
 
 int64_t tag_launch_count(const tag_handle* h) { return h ? h->launches : 0; }

@@ -1,0 +1,505 @@
+// Fused tail of one post-norm transformer layer on sm_100a (reference model.py:143-146, nn.TransformerEncoderLayer with
+// norm_first = False, ReLU, eps 1e-5):
+//
+//     x1 = LayerNorm1(x + attn @ Wo^T + bo)            (out-proj + residual + norm1)
+//     x  = LayerNorm2(x1 + relu(x1 @ W1^T + b1) @ W2^T + b2)     (FFN + residual + norm2)
+//
+// as ONE persistent tcgen05 kernel per layer instead of three GEMM launches. Per 256-row tile (CTA pair, cta_group::2):
+//
+//   TMEM   cols   0..255  ACC_O : out-proj accumulator -> x1 (fp32, parked with tcgen05.st) -> FFN2 accumulates ON TOP of it
+//          cols 256..511  ACC_H : two 128-column halves, the FFN1 accumulators of hidden chunks i and i+1
+//   SMEM   XA   64 KiB    x1 as the fp16 A operand of FFN1 (written by the LayerNorm1 epilogue in the 128B-swizzled K-major layout)
+//          HB   2 x 32 KiB relu(h) chunks (128 hidden columns) as the fp16 A operand of FFN2, double buffered
+//          RING 4 x 16 KiB TMA slots: attention tile + Wo (out-proj), W1 row blocks, W2 column blocks
+//
+// The [rows x 1024] FFN hidden state, x1 and its fp16 copy never touch HBM: per layer pass the kernel reads attn (fp16) and x
+// (fp32) and writes x (fp32) and its fp16 copy — 1.27 GB for 412,500 tokens instead of 4.1 GB for the three launches it replaces.
+// Hidden chunks are software pipelined: while the tensor pipe runs FFN2 of chunk i-1 and FFN1 of chunk i+1, the epilogue
+// warps turn chunk i (TMEM -> +b1 -> ReLU -> fp16 -> SMEM) around.
+//
+// Roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (leader CTA), warps 2..17 epilogue
+// (4 per TMEM lane quarter x 4 column groups). Barrier protocol in the comments of each role; every wait is bounded.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tcx;
+
+constexpr int BM = 128, BK = 64, UK = 16, DM = 256;
+constexpr int SUB = BM * BK * 2;                 // 16 KiB: one [128 x 64] fp16 sub-tile, SWIZZLE_128B K-major
+constexpr int NS = 4;                            // ring slots of SUB bytes
+constexpr int HCOLS = 128;                       // hidden columns per chunk
+constexpr int EPI_WARPS = 16;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int CW = 16;
+constexpr int OFF_XA = 0, OFF_HB = 4 * SUB, OFF_RING = 8 * SUB, OFF_BAR = OFF_RING + NS * SUB;
+constexpr int BAR_BYTES = 512;
+constexpr int RED_BYTES = 2 * EPI_WARPS * 32 * 8;          // LN1 / LN2 (sum, sumsq) exchange
+constexpr int PAR_FLOATS = 6 * DM;                         // bo, b2, ln1 gamma/beta, ln2 gamma/beta
+constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + RED_BYTES + PAR_FLOATS * 4 + 1024;
+constexpr int STG_WARP_BYTES = 32 * 64;
+static_assert(EPI_WARPS * STG_WARP_BYTES <= 4 * SUB, "the epilogue staging tiles alias the h buffers");
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr int TMEM_COLS = 512;
+constexpr uint32_t IDESC_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // f16 x f16 -> f32, M = 256 (pair)
+constexpr uint32_t IDESC_N128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+// barrier slots (8 B each)
+constexpr int B_RFULL = 0, B_REMPTY = NS, B_OFULL = 2 * NS, B_X1 = 2 * NS + 1, B_HFULL = 2 * NS + 2, B_HREADY = 2 * NS + 4,
+              B_HBFREE = 2 * NS + 6, B_O2FULL = 2 * NS + 8, B_OFREE = 2 * NS + 9, B_COUNT = 2 * NS + 10;
+
+struct TlParams {
+  int64_t M;              // token rows
+  int64_t m_tiles;
+  int n_chunks;           // ffn_dim / 128 (even)
+  const float* x_in;      // [M,256] fp32 residual stream (read)
+  float* x_out;           // [M,256] fp32 (written; may alias x_in: a tile reads its rows before it writes them)
+  __half* x16_out;        // [M,256] fp16 copy of x_out
+  const float* bo; const float* b1; const float* b2;
+  const float* ln1_g; const float* ln1_b; const float* ln2_g; const float* ln2_b;
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
+              const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TlParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t xa = base + OFF_XA, hb = base + OFF_HB, ring = base + OFF_RING, bars = base + OFF_BAR;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  const uint32_t tmem_slot = bars + 8u * B_COUNT;
+  const uint32_t red0 = bars + BAR_BYTES;
+  float* s_par = reinterpret_cast<float*>(smem_raw + (bars - smem_u32(smem_raw)) + BAR_BYTES + RED_BYTES);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HC = p.n_chunks >> 1;               // completions per tile of every per-buffer barrier
+
+  for (int i = threadIdx.x; i < DM; i += THREADS) {
+    s_par[i] = __ldg(p.bo + i); s_par[DM + i] = __ldg(p.b2 + i);
+    s_par[2 * DM + i] = __ldg(p.ln1_g + i); s_par[3 * DM + i] = __ldg(p.ln1_b + i);
+    s_par[4 * DM + i] = __ldg(p.ln2_g + i); s_par[5 * DM + i] = __ldg(p.ln2_b + i);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(bar(B_RFULL + s), 1); mbar_init(bar(B_REMPTY + s), 1); }
+    mbar_init(bar(B_OFULL), 1);
+    mbar_init(bar(B_X1), EPI_WARPS * 2);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(B_HFULL + b), 1); mbar_init(bar(B_HREADY + b), EPI_WARPS * 2); mbar_init(bar(B_HBFREE + b), 1); }
+    mbar_init(bar(B_O2FULL), 1);
+    mbar_init(bar(B_OFREE), EPI_WARPS * 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int64_t total_tiles = (p.m_tiles + 1) / 2;
+  const int64_t tile0 = (int64_t)(blockIdx.x >> 1), tile_step = (int64_t)(gridDim.x >> 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer: the loads of a tile in exactly the order the MMA issuer consumes them =================
+      int slot = 0; uint32_t phase = 0;
+      auto acquire = [&](uint32_t bytes_both) {          // wait for the slot, arm its full barrier (leader: bytes of both CTAs)
+        mbar_wait(bar(B_REMPTY + slot), phase ^ 1u);
+        if (leader) mbar_arrive_expect_tx(bar(B_RFULL + slot), bytes_both);
+        return ring + (uint32_t)(slot * SUB);
+      };
+      auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1u; } };
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int m_tile = (int)(tile * 2 + rank);
+        for (int kb = 0; kb < DM / BK; ++kb) {             // out-proj: attention rows, then this CTA's half of Wo
+          uint32_t d = acquire(2u * SUB);
+          tma_load_3d_pair(d, &map_att, bar(B_RFULL + slot), kb * BK, m_tile * BM, 0);
+          advance();
+          d = acquire(2u * SUB);
+          tma_load_2d_pair(d, &map_wo, bar(B_RFULL + slot), kb * BK, (int)rank * (DM / 2));
+          advance();
+        }
+        auto load_f1 = [&](int j) {                        // W1 rows of hidden chunk j: 64 per CTA
+          for (int kb = 0; kb < DM / BK; ++kb) {
+            const uint32_t d = acquire(2u * (SUB / 2));
+            tma_load_2d_pair(d, &map_w1, bar(B_RFULL + slot), kb * BK, j * HCOLS + (int)rank * (HCOLS / 2));
+            advance();
+          }
+        };
+        load_f1(0);
+        load_f1(1);
+        for (int i = 0; i < p.n_chunks; ++i) {
+          for (int kb = 0; kb < HCOLS / BK; ++kb) {        // W2 columns of hidden chunk i: 128 output rows per CTA
+            const uint32_t d = acquire(2u * SUB);
+            tma_load_2d_pair(d, &map_w2, bar(B_RFULL + slot), i * HCOLS + kb * BK, (int)rank * (DM / 2));
+            advance();
+          }
+          if (i + 2 < p.n_chunks) load_f1(i + 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ================= MMA issuer (leader CTA) =================
+      int slot = 0; uint32_t phase = 0;
+      auto wait_full = [&]() {                              // the slot's TMA bytes (of both CTAs) have landed
+        mbar_wait(bar(B_RFULL + slot), phase);
+        tc_fence_after();
+        return ring + (uint32_t)(slot * SUB);
+      };
+      auto next = [&]() { const int cur = slot; if (++slot == NS) { slot = 0; phase ^= 1u; } return cur; };
+      const uint32_t acc_o = tmem_base, acc_h = tmem_base + 256u;
+      int64_t it = 0;
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+        if (it > 0) { mbar_wait(bar(B_OFREE), (uint32_t)((it - 1) & 1)); tc_fence_after(); }   // LayerNorm2 of the previous tile has drained ACC_O
+        // ---- out-proj: ACC_O = attn @ Wo^T
+        for (int kb = 0; kb < DM / BK; ++kb) {
+          const uint32_t sa = wait_full();
+          const int slot_a = next();
+          const uint32_t sb = wait_full();
+          const int slot_b = next();
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_f16_pair(acc_o, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(bar(B_REMPTY + slot_a));          // both slots are free (in both CTAs) once these MMAs retire
+          umma_commit_pair(bar(B_REMPTY + slot_b));
+        }
+        umma_commit_pair(bar(B_OFULL));
+        // ---- x1 (fp16, SMEM) and its fp32 copy parked in ACC_O are ready
+        mbar_wait(bar(B_X1), (uint32_t)(it & 1));
+        tc_fence_after();
+        auto ffn1 = [&](int j) {                           // ACC_H[j & 1] = x1 @ W1[chunk j]^T   (N = 128)
+          const uint32_t d = acc_h + (uint32_t)((j & 1) * HCOLS);
+          for (int kb = 0; kb < DM / BK; ++kb) {
+            const uint32_t sb = wait_full();
+            const int sl = next();
+            const uint64_t adesc = make_smem_desc(xa + (uint32_t)(kb * SUB)), bdesc = make_smem_desc(sb);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              umma_f16_pair(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N128, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(bar(B_REMPTY + sl));
+          }
+          umma_commit_pair(bar(B_HFULL + (j & 1)));
+        };
+        ffn1(0);
+        ffn1(1);
+        for (int i = 0; i < p.n_chunks; ++i) {
+          const int b = i & 1;
+          // relu(h_i) is in HB[b] (and ACC_H[b] has been read): FFN2 accumulates on top of the parked x1
+          mbar_wait(bar(B_HREADY + b), (uint32_t)((it * HC + (i >> 1)) & 1));
+          tc_fence_after();
+          for (int kb = 0; kb < HCOLS / BK; ++kb) {
+            const uint32_t sb = wait_full();
+            const int sl = next();
+            const uint64_t adesc = make_smem_desc(hb + (uint32_t)((b * 2 + kb) * SUB)), bdesc = make_smem_desc(sb);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k)
+              umma_f16_pair(acc_o, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, 1u);
+            umma_commit_pair(bar(B_REMPTY + sl));
+          }
+          umma_commit_pair(bar(B_HBFREE + b));
+          if (i + 2 < p.n_chunks) ffn1(i + 2);
+        }
+        umma_commit_pair(bar(B_O2FULL));
+      }
+    }
+  } else {
+    // ================= epilogue warps =================
+    const int q = warp & 3;                      // TMEM lane quarter
+    const int part = (warp - 2) >> 2;            // column group: 64 of the 256 output columns, 32 of a 128-column hidden chunk
+    constexpr int NCH = 64 / CW;
+    const uint32_t stg = hb + (uint32_t)((warp - 2) * STG_WARP_BYTES);     // aliases HB: only used while no h chunk is live
+    const int row = q * 32 + lane;               // this lane's row of the CTA's 128-row tile
+    const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64);
+    const uint32_t t_h = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(part * 32);
+    const int nl = part * 64;
+    const uint32_t xa_row = xa + (uint32_t)(part * SUB) + (uint32_t)(row * 128);
+    int64_t it = 0;
+    for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int64_t m_tile = tile * 2 + rank;
+      const RowMap rm{m_tile * BM, q * 32, 0, 0};
+      // ---------------- LayerNorm1: x1 = LN(acc + bo + x) -> parked in ACC_O (fp32) and written to XA (fp16 A operand)
+      {
+        float s1 = 0.f, s2 = 0.f;
+        uint4 rres[4];
+        unit_load(reinterpret_cast<const char*>(p.x_in), (int64_t)DM * 4, rm, p.M, (int64_t)nl * 4, lane, rres);
+        mbar_wait(bar(B_OFULL), (uint32_t)(it & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          unit_to_smem(stg, lane, rres);
+          __syncwarp();
+          if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.x_in), (int64_t)DM * 4, rm, p.M, (int64_t)(nl + (u + 1) * CW) * 4, lane, rres);
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 xr = lds128(stg_addr(stg, lane, i));
+            const float4 bb = *reinterpret_cast<const float4*>(s_par + nl + u * CW + i * 4);
+            const float v0 = __uint_as_float(raw[i * 4]) + bb.x + __uint_as_float(xr.x);
+            const float v1 = __uint_as_float(raw[i * 4 + 1]) + bb.y + __uint_as_float(xr.y);
+            const float v2 = __uint_as_float(raw[i * 4 + 2]) + bb.z + __uint_as_float(xr.z);
+            const float v3 = __uint_as_float(raw[i * 4 + 3]) + bb.w + __uint_as_float(xr.w);
+            s1 += (v0 + v1) + (v2 + v3);
+            s2 = fmaf(v0, v0, s2); s2 = fmaf(v1, v1, s2); s2 = fmaf(v2, v2, s2); s2 = fmaf(v3, v3, s2);
+            raw[i * 4] = __float_as_uint(v0); raw[i * 4 + 1] = __float_as_uint(v1);
+            raw[i * 4 + 2] = __float_as_uint(v2); raw[i * 4 + 3] = __float_as_uint(v3);
+          }
+          tmem_st16(t_o + (uint32_t)(u * CW), raw);
+          __syncwarp();
+        }
+        tmem_st_wait();
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red0 + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
+        float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < EPI_WARPS / 4; ++pp) {
+          const int e = pp * 4 + ((q - 2) & 3);
+          float a, b;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red0 + (uint32_t)((e * 32 + lane) * 8)) : "memory");
+          S1 += a; S2 += b;
+        }
+        const float mean = S1 * (1.0f / DM);
+        const float var = fmaxf(S2 * (1.0f / DM) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+          float y[CW];
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(s_par + 2 * DM + nl + u * CW + i);
+            const float4 b = *reinterpret_cast<const float4*>(s_par + 3 * DM + nl + u * CW + i);
+            y[i] = fmaf(fmaf(__uint_as_float(raw[i]), rstd, nmr), g.x, b.x);
+            y[i + 1] = fmaf(fmaf(__uint_as_float(raw[i + 1]), rstd, nmr), g.y, b.y);
+            y[i + 2] = fmaf(fmaf(__uint_as_float(raw[i + 2]), rstd, nmr), g.z, b.z);
+            y[i + 3] = fmaf(fmaf(__uint_as_float(raw[i + 3]), rstd, nmr), g.w, b.w);
+          }
+#pragma unroll
+          for (int i = 0; i < CW; ++i) raw[i] = __float_as_uint(y[i]);
+          tmem_st16(t_o + (uint32_t)(u * CW), raw);         // x1 (fp32) stays in the accumulator: FFN2 adds onto it
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {                      // x1 (fp16) -> XA sub-tile `part`, 16-byte chunks u*2 + c
+            uint4 o;
+            __half2* hh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(y[c * 8 + 2 * e], y[c * 8 + 2 * e + 1]);
+            sts128(xa_row + (uint32_t)((((u * 2 + c) ^ (row & 7)) & 7) << 4), o);
+          }
+        }
+        tmem_st_wait();
+        fence_async_smem();                                  // generic-proxy SMEM writes -> visible to tcgen05.mma (async proxy)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar(B_X1));
+      }
+      // ---------------- hidden chunks: relu(ACC_H + b1) -> fp16 -> HB (A operand of FFN2)
+      for (int i = 0; i < p.n_chunks; ++i) {
+        const int b = i & 1;
+        const int64_t seq = it * HC + (i >> 1);              // completions of this buffer's barriers before this chunk
+        mbar_wait(bar(B_HFULL + b), (uint32_t)(seq & 1));
+        tc_fence_after();
+        uint32_t r0[CW], r1[CW];
+        tmem_ld16_issue(t_h + (uint32_t)(b * HCOLS), r0);
+        tmem_ld16_issue(t_h + (uint32_t)(b * HCOLS + CW), r1);
+        tmem_ld16_wait(r0);
+        tmem_ld16_wait(r1);
+        const float* b1 = p.b1 + i * HCOLS + part * 32;
+        uint4 o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t* src = c < 2 ? r0 : r1;
+          const int off = (c & 1) * 8;
+          const float4 ba = __ldg(reinterpret_cast<const float4*>(b1 + c * 8));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + c * 8 + 4));
+          __half2* hh = reinterpret_cast<__half2*>(&o[c]);
+          hh[0] = __floats2half2_rn(fmaxf(__uint_as_float(src[off]) + ba.x, 0.f), fmaxf(__uint_as_float(src[off + 1]) + ba.y, 0.f));
+          hh[1] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(src[off + 3]) + ba.w, 0.f));
+          hh[2] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(src[off + 5]) + bb.y, 0.f));
+          hh[3] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(src[off + 7]) + bb.w, 0.f));
+        }
+        if (seq > 0) mbar_wait(bar(B_HBFREE + b), (uint32_t)((seq - 1) & 1));     // FFN2 of chunk i-2 has finished reading HB[b]
+        const uint32_t hrow = hb + (uint32_t)((b * 2 + (part >> 1)) * SUB) + (uint32_t)(row * 128);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128(hrow + (uint32_t)(((((part & 1) * 4 + c) ^ (row & 7)) & 7) << 4), o[c]);
+        fence_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(bar(B_HREADY + b));
+      }
+      // ---------------- LayerNorm2: x = LN(acc + b2) (acc already holds x1 + FFN) -> fp32 stream + fp16 copy
+      {
+        float s1 = 0.f, s2 = 0.f;
+        mbar_wait(bar(B_O2FULL), (uint32_t)(it & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(s_par + DM + nl + u * CW + i);
+            const float v0 = __uint_as_float(raw[i]) + bb.x, v1 = __uint_as_float(raw[i + 1]) + bb.y;
+            const float v2 = __uint_as_float(raw[i + 2]) + bb.z, v3 = __uint_as_float(raw[i + 3]) + bb.w;
+            s1 += (v0 + v1) + (v2 + v3);
+            s2 = fmaf(v0, v0, s2); s2 = fmaf(v1, v1, s2); s2 = fmaf(v2, v2, s2); s2 = fmaf(v3, v3, s2);
+            raw[i] = __float_as_uint(v0); raw[i + 1] = __float_as_uint(v1); raw[i + 2] = __float_as_uint(v2); raw[i + 3] = __float_as_uint(v3);
+          }
+          tmem_st16(t_o + (uint32_t)(u * CW), raw);
+        }
+        tmem_st_wait();
+        const uint32_t red1 = red0 + (uint32_t)(EPI_WARPS * 32 * 8);
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red1 + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
+        float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < EPI_WARPS / 4; ++pp) {
+          const int e = pp * 4 + ((q - 2) & 3);
+          float a, b;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red1 + (uint32_t)((e * 32 + lane) * 8)) : "memory");
+          S1 += a; S2 += b;
+        }
+        const float mean = S1 * (1.0f / DM);
+        const float var = fmaxf(S2 * (1.0f / DM) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        const float nmr = -mean * rstd;
+        uint32_t h16[CW];
+#pragma unroll
+        for (int u = 0; u < NCH; ++u) {
+          uint32_t raw[CW];
+          tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
+          tmem_ld16_wait(raw);
+          if (u == NCH - 1) {                                 // last TMEM read of the tile: ACC_O may be overwritten
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(bar(B_OFREE));
+          }
+          float y[CW];
+#pragma unroll
+          for (int i = 0; i < CW; i += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(s_par + 4 * DM + nl + u * CW + i);
+            const float4 b = *reinterpret_cast<const float4*>(s_par + 5 * DM + nl + u * CW + i);
+            y[i] = fmaf(fmaf(__uint_as_float(raw[i]), rstd, nmr), g.x, b.x);
+            y[i + 1] = fmaf(fmaf(__uint_as_float(raw[i + 1]), rstd, nmr), g.y, b.y);
+            y[i + 2] = fmaf(fmaf(__uint_as_float(raw[i + 2]), rstd, nmr), g.z, b.z);
+            y[i + 3] = fmaf(fmaf(__uint_as_float(raw[i + 3]), rstd, nmr), g.w, b.w);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(stg_addr(stg, lane, i), make_uint4(__float_as_uint(y[i * 4]), __float_as_uint(y[i * 4 + 1]),
+                                                      __float_as_uint(y[i * 4 + 2]), __float_as_uint(y[i * 4 + 3])));
+#pragma unroll
+          for (int i = 0; i < CW / 2; ++i) {
+            const __half2 t = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+            h16[(u & 1) * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&t);
+          }
+          __syncwarp();
+          unit_store(reinterpret_cast<char*>(p.x_out), (int64_t)DM * 4, rm, p.M, (int64_t)(nl + u * CW) * 4, lane, stg);
+          __syncwarp();
+          if (u & 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sts128(stg_addr(stg, lane, i), make_uint4(h16[i * 4], h16[i * 4 + 1], h16[i * 4 + 2], h16[i * 4 + 3]));
+            __syncwarp();
+            unit_store(reinterpret_cast<char*>(p.x16_out), (int64_t)DM * 2, rm, p.M, (int64_t)(nl + (u - 1) * CW) * 2, lane, stg);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+bool tlayer_tail_supported(int64_t M, int ffn_dim) { return M > 128 && ffn_dim >= 256 && ffn_dim % 256 == 0; }
+
+cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t, cudaStream_t s, char* err, int errlen) {
+  if (t.M <= 0) return cudaSuccess;
+  auto bad = [&](const char* msg) {
+    snprintf(err, errlen, "tlayer_tail: %s (M=%lld ffn=%d)", msg, (long long)t.M, t.ffn_dim);
+    return cudaErrorInvalidValue;
+  };
+  if (!tlayer_tail_supported(t.M, t.ffn_dim)) return bad("needs more than 128 rows and ffn_dim a multiple of 256");
+  if (!t.att16 || !t.x32 || !t.x16 || !t.Wo16 || !t.W1_16 || !t.W2_16 || !t.bo || !t.b1 || !t.b2 || !t.ln1_g || !t.ln1_b || !t.ln2_g || !t.ln2_b)
+    return bad("NULL argument");
+  if ((reinterpret_cast<uintptr_t>(t.att16) | reinterpret_cast<uintptr_t>(t.x32) | reinterpret_cast<uintptr_t>(t.x16) |
+       reinterpret_cast<uintptr_t>(t.Wo16) | reinterpret_cast<uintptr_t>(t.W1_16) | reinterpret_cast<uintptr_t>(t.W2_16) |
+       reinterpret_cast<uintptr_t>(t.b1)) & 15)
+    return bad("pointers must be 16-byte aligned");
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_tlayer_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(k_tlayer_tail, smem=%d) failed: %s", SMEM_BYTES, cudaGetErrorString(e)); return e; }
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(encode_fn);
+  CUtensorMap m_att, m_wo, m_w1, m_w2;
+  cuuint32_t es3[3] = {1, 1, 1}, es2[2] = {1, 1};
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)DM, (cuuint64_t)t.M, 1}, gstr[2] = {(cuuint64_t)DM * 2, (cuuint64_t)t.M * DM * 2};
+    cuuint32_t box[3] = {BK, BM, 1};
+    CUresult r = encode(&m_att, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(t.att16), gdim, gstr, box, es3,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(attn) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
+  }
+  auto wmap = [&](CUtensorMap* m, const __half* W, int K, int N, int box_rows) {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N}, gstr[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(W), gdim, gstr, box, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  };
+  CUresult r = wmap(&m_wo, t.Wo16, DM, DM, DM / 2);
+  if (r == CUDA_SUCCESS) r = wmap(&m_w1, t.W1_16, DM, t.ffn_dim, HCOLS / 2);
+  if (r == CUDA_SUCCESS) r = wmap(&m_w2, t.W2_16, t.ffn_dim, DM, DM / 2);
+  if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
+
+  TlParams p{};
+  p.M = t.M; p.m_tiles = (t.M + BM - 1) / BM; p.n_chunks = t.ffn_dim / HCOLS;
+  p.x_in = t.x32; p.x_out = t.x32; p.x16_out = t.x16;
+  p.bo = t.bo; p.b1 = t.b1; p.b2 = t.b2; p.ln1_g = t.ln1_g; p.ln1_b = t.ln1_b; p.ln2_g = t.ln2_g; p.ln2_b = t.ln2_b;
+  const int64_t total = (p.m_tiles + 1) / 2;
+  const int64_t clusters = total < num_sms / 2 ? total : num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_tlayer_tail, m_att, m_wo, m_w1, m_w2, p);
+}
