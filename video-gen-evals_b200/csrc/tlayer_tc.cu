@@ -6,11 +6,12 @@
 //
 // as ONE persistent tcgen05 kernel per layer instead of three GEMM launches. Per 256-row tile (CTA pair, cta_group::2):
 //
-//   TMEM   cols   0..255  ACC_O : out-proj accumulator -> x1 (fp32, parked with tcgen05.st) -> FFN2 accumulates ON TOP of it
-//          cols 256..511  ACC_H : two 128-column halves, the FFN1 accumulators of hidden chunks i and i+1
+//   TMEM   cols   0..255  ACC_O : x1 (fp32, parked by the LayerNorm1 epilogue with tcgen05.st); FFN2 accumulates ON TOP of it
+//          cols 256..511  ACC_H : the out-proj accumulator of the NEXT tile (issued while LayerNorm2 of this tile still reads
+//                                 ACC_O), then two 128-column halves: the FFN1 accumulators of hidden chunks i and i+1
 //   SMEM   XA   64 KiB    x1 as the fp16 A operand of FFN1 (written by the LayerNorm1 epilogue in the 128B-swizzled K-major layout)
 //          HB   2 x 32 KiB relu(h) chunks (128 hidden columns) as the fp16 A operand of FFN2, double buffered
-//          RING 4 x 16 KiB TMA slots: attention tile + Wo (out-proj), W1 row blocks, W2 column blocks
+//          RING 10 x 8 KiB TMA granules: attention tile + Wo (out-proj), W1 row blocks, W2 column blocks
 //
 // The [rows x 1024] FFN hidden state, x1 and its fp16 copy never touch HBM: per layer pass the kernel reads attn (fp16) and x
 // (fp32) and writes x (fp32) and its fp16 copy — 1.27 GB for 412,500 tokens instead of 4.1 GB for the three launches it replaces.
@@ -35,15 +36,19 @@ using namespace tcx;
 
 constexpr int BM = 128, BK = 64, UK = 16, DM = 256;
 constexpr int SUB = BM * BK * 2;                 // 16 KiB: one [128 x 64] fp16 sub-tile, SWIZZLE_128B K-major
-constexpr int NS = 4;                            // ring slots of SUB bytes
+constexpr int UNIT = SUB / 2;                    // ring granule: 8 KiB (a W1 block); attention / Wo / W2 blocks take two
+constexpr int NS = 10;                           // ring granules (80 KiB). Two-granule loads always start on an even granule
+                                                 // (single-granule loads come in fours), so they never straddle the wrap
 constexpr int HCOLS = 128;                       // hidden columns per chunk
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int CW = 16;
-constexpr int OFF_XA = 0, OFF_HB = 4 * SUB, OFF_RING = 8 * SUB, OFF_BAR = OFF_RING + NS * SUB;
+constexpr int OFF_XA = 0, OFF_HB = 4 * SUB, OFF_RING = 8 * SUB, OFF_BAR = OFF_RING + NS * UNIT;
 constexpr int BAR_BYTES = 512;
-constexpr int RED_BYTES = 2 * EPI_WARPS * 32 * 8;          // LN1 / LN2 (sum, sumsq) exchange
-constexpr int PAR_FLOATS = 6 * DM;                         // bo, b2, ln1 gamma/beta, ln2 gamma/beta
+constexpr int RED_BYTES = EPI_WARPS * 32 * 8;              // (sum, sumsq) exchange of LN1 and LN2 (one buffer: every use is fenced
+                                                           // from the next by a barrier that needs all epilogue warps)
+constexpr int MAX_FFN = 1024;
+constexpr int PAR_FLOATS = 6 * DM + MAX_FFN;               // bo, b2, ln1 gamma/beta, ln2 gamma/beta, b1
 constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + RED_BYTES + PAR_FLOATS * 4 + 1024;
 constexpr int STG_WARP_BYTES = 32 * 64;
 static_assert(EPI_WARPS * STG_WARP_BYTES <= 4 * SUB, "the epilogue staging tiles alias the h buffers");
@@ -69,6 +74,19 @@ struct TlParams {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifdef TAG_EXPERIMENTS
+// timeline probe (tools/tl_trace.py): CTA 0's MMA thread / first epilogue warp / producer append (tag, clock64) pairs
+__device__ long long* g_tl_trace = nullptr;
+#define TL_TRACE(role, tag)                                                                       \
+  do {                                                                                            \
+    if (g_tl_trace != nullptr && blockIdx.x == 0 && tr_n < 2000) {                                \
+      g_tl_trace[(role) * 4096 + 2 * tr_n] = (tag); g_tl_trace[(role) * 4096 + 2 * tr_n + 1] = clock64(); ++tr_n; \
+    }                                                                                             \
+  } while (0)
+#else
+#define TL_TRACE(role, tag) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(THREADS, 1)
 k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TlParams p) {
@@ -89,13 +107,14 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
     s_par[2 * DM + i] = __ldg(p.ln1_g + i); s_par[3 * DM + i] = __ldg(p.ln1_b + i);
     s_par[4 * DM + i] = __ldg(p.ln2_g + i); s_par[5 * DM + i] = __ldg(p.ln2_b + i);
   }
+  for (int i = threadIdx.x; i < p.n_chunks * HCOLS; i += THREADS) s_par[6 * DM + i] = __ldg(p.b1 + i);   // a global load per chunk sat on the
+                                                                                                       // chunk turn-around path (ncu: 55 % of it)
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(bar(B_RFULL + s), 1); mbar_init(bar(B_REMPTY + s), 1); }
     mbar_init(bar(B_OFULL), 1);
     mbar_init(bar(B_X1), EPI_WARPS * 2);
     for (int b = 0; b < 2; ++b) { mbar_init(bar(B_HFULL + b), 1); mbar_init(bar(B_HREADY + b), EPI_WARPS * 2); mbar_init(bar(B_HBFREE + b), 1); }
     mbar_init(bar(B_O2FULL), 1);
-    mbar_init(bar(B_OFREE), EPI_WARPS * 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -116,36 +135,40 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
     if (lane == 0) {
       // ================= TMA producer: the loads of a tile in exactly the order the MMA issuer consumes them =================
       int slot = 0; uint32_t phase = 0;
-      auto acquire = [&](uint32_t bytes_both) {          // wait for the slot, arm its full barrier (leader: bytes of both CTAs)
-        mbar_wait(bar(B_REMPTY + slot), phase ^ 1u);
-        if (leader) mbar_arrive_expect_tx(bar(B_RFULL + slot), bytes_both);
-        return ring + (uint32_t)(slot * SUB);
+      int tr_n = 0; (void)tr_n;
+      auto acquire = [&](int n_units) {                    // wait for n granules, arm the load's full barrier (leader: bytes of both CTAs)
+        for (int u = 0; u < n_units; ++u) mbar_wait(bar(B_REMPTY + slot + u), phase ^ 1u);
+        if (leader) mbar_arrive_expect_tx(bar(B_RFULL + slot), 2u * (uint32_t)(n_units * UNIT));
+        return ring + (uint32_t)(slot * UNIT);
       };
-      auto advance = [&]() { if (++slot == NS) { slot = 0; phase ^= 1u; } };
+      auto advance = [&](int n_units) { slot += n_units; if (slot >= NS) { slot = 0; phase ^= 1u; } };
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         const int m_tile = (int)(tile * 2 + rank);
         for (int kb = 0; kb < DM / BK; ++kb) {             // out-proj: attention rows, then this CTA's half of Wo
-          uint32_t d = acquire(2u * SUB);
+          uint32_t d = acquire(2);
           tma_load_3d_pair(d, &map_att, bar(B_RFULL + slot), kb * BK, m_tile * BM, 0);
-          advance();
-          d = acquire(2u * SUB);
+          TL_TRACE(2, 100 + kb);
+          advance(2);
+          d = acquire(2);
           tma_load_2d_pair(d, &map_wo, bar(B_RFULL + slot), kb * BK, (int)rank * (DM / 2));
-          advance();
+          advance(2);
         }
         auto load_f1 = [&](int j) {                        // W1 rows of hidden chunk j: 64 per CTA
           for (int kb = 0; kb < DM / BK; ++kb) {
-            const uint32_t d = acquire(2u * (SUB / 2));
+            const uint32_t d = acquire(1);
             tma_load_2d_pair(d, &map_w1, bar(B_RFULL + slot), kb * BK, j * HCOLS + (int)rank * (HCOLS / 2));
-            advance();
+            TL_TRACE(2, 200 + j * 4 + kb);
+            advance(1);
           }
         };
         load_f1(0);
         load_f1(1);
         for (int i = 0; i < p.n_chunks; ++i) {
           for (int kb = 0; kb < HCOLS / BK; ++kb) {        // W2 columns of hidden chunk i: 128 output rows per CTA
-            const uint32_t d = acquire(2u * SUB);
+            const uint32_t d = acquire(2);
             tma_load_2d_pair(d, &map_w2, bar(B_RFULL + slot), i * HCOLS + kb * BK, (int)rank * (DM / 2));
-            advance();
+            TL_TRACE(2, 300 + i * 2 + kb);
+            advance(2);
           }
           if (i + 2 < p.n_chunks) load_f1(i + 2);
         }
@@ -155,45 +178,57 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
     if (lane == 0 && leader) {
       // ================= MMA issuer (leader CTA) =================
       int slot = 0; uint32_t phase = 0;
-      auto wait_full = [&]() {                              // the slot's TMA bytes (of both CTAs) have landed
-        mbar_wait(bar(B_RFULL + slot), phase);
+      int tr_n = 0; (void)tr_n;
+      uint32_t full_par = 0;                                // a load's full barrier is the one of its FIRST granule: a granule that was the
+                                                            // second half of a two-granule load skipped a use, so every full barrier keeps
+                                                            // its own parity (the empty barriers are used by every granule on every lap)
+      auto wait_full = [&]() {                              // the load's TMA bytes (of both CTAs) have landed
+        mbar_wait(bar(B_RFULL + slot), (full_par >> slot) & 1u);
+        full_par ^= 1u << slot;
         tc_fence_after();
-        return ring + (uint32_t)(slot * SUB);
+        return ring + (uint32_t)(slot * UNIT);
       };
-      auto next = [&]() { const int cur = slot; if (++slot == NS) { slot = 0; phase ^= 1u; } return cur; };
+      auto next = [&](int n_units) { const int cur = slot; slot += n_units; if (slot >= NS) { slot = 0; phase ^= 1u; } return cur; };
+      auto release = [&](int first, int n_units) {          // granules are free (in both CTAs) once the MMAs issued so far retire
+        for (int u = 0; u < n_units; ++u) umma_commit_pair(bar(B_REMPTY + first + u));
+      };
       const uint32_t acc_o = tmem_base, acc_h = tmem_base + 256u;
       int64_t it = 0;
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
-        if (it > 0) { mbar_wait(bar(B_OFREE), (uint32_t)((it - 1) & 1)); tc_fence_after(); }   // LayerNorm2 of the previous tile has drained ACC_O
-        // ---- out-proj: ACC_O = attn @ Wo^T
+        // ---- out-proj: ACC_H (all 256 columns) = attn @ Wo^T. ACC_H is free: every hidden chunk of the previous tile has been
+        // read (h_ready waits above); ACC_O may still be read by LayerNorm2 of the previous tile — nothing touches it here
         for (int kb = 0; kb < DM / BK; ++kb) {
           const uint32_t sa = wait_full();
-          const int slot_a = next();
+          const int slot_a = next(2);
           const uint32_t sb = wait_full();
-          const int slot_b = next();
+          const int slot_b = next(2);
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k)
-            umma_f16_pair(acc_o, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(bar(B_REMPTY + slot_a));          // both slots are free (in both CTAs) once these MMAs retire
-          umma_commit_pair(bar(B_REMPTY + slot_b));
+            umma_f16_pair(acc_h, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, (kb | k) != 0 ? 1u : 0u);
+          release(slot_a, 2);
+          release(slot_b, 2);
         }
         umma_commit_pair(bar(B_OFULL));
-        // ---- x1 (fp16, SMEM) and its fp32 copy parked in ACC_O are ready
+        TL_TRACE(0, 1);
+        // ---- x1 (fp16, SMEM) and its fp32 copy parked in ACC_O are ready; every epilogue warp has left LayerNorm2 of the
+        // previous tile (ACC_O is ours) and LayerNorm1 of this one (ACC_H is free for the hidden chunks)
         mbar_wait(bar(B_X1), (uint32_t)(it & 1));
         tc_fence_after();
+        TL_TRACE(0, 2);
         auto ffn1 = [&](int j) {                           // ACC_H[j & 1] = x1 @ W1[chunk j]^T   (N = 128)
           const uint32_t d = acc_h + (uint32_t)((j & 1) * HCOLS);
           for (int kb = 0; kb < DM / BK; ++kb) {
             const uint32_t sb = wait_full();
-            const int sl = next();
+            const int sl = next(1);
             const uint64_t adesc = make_smem_desc(xa + (uint32_t)(kb * SUB)), bdesc = make_smem_desc(sb);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k)
               umma_f16_pair(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N128, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_pair(bar(B_REMPTY + sl));
+            release(sl, 1);
           }
           umma_commit_pair(bar(B_HFULL + (j & 1)));
+          TL_TRACE(0, 200 + j);
         };
         ffn1(0);
         ffn1(1);
@@ -202,19 +237,22 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           // relu(h_i) is in HB[b] (and ACC_H[b] has been read): FFN2 accumulates on top of the parked x1
           mbar_wait(bar(B_HREADY + b), (uint32_t)((it * HC + (i >> 1)) & 1));
           tc_fence_after();
+          TL_TRACE(0, 300 + i);
           for (int kb = 0; kb < HCOLS / BK; ++kb) {
             const uint32_t sb = wait_full();
-            const int sl = next();
+            const int sl = next(2);
             const uint64_t adesc = make_smem_desc(hb + (uint32_t)((b * 2 + kb) * SUB)), bdesc = make_smem_desc(sb);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k)
               umma_f16_pair(acc_o, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, 1u);
-            umma_commit_pair(bar(B_REMPTY + sl));
+            release(sl, 2);
           }
           umma_commit_pair(bar(B_HBFREE + b));
+          TL_TRACE(0, 400 + i);
           if (i + 2 < p.n_chunks) ffn1(i + 2);
         }
         umma_commit_pair(bar(B_O2FULL));
+        TL_TRACE(0, 9);
       }
     }
   } else {
@@ -226,26 +264,31 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
     const int row = q * 32 + lane;               // this lane's row of the CTA's 128-row tile
     const uint32_t t_o = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 64);
     const uint32_t t_h = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(part * 32);
+    const uint32_t t_p = tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(part * 64);      // out-proj accumulator (in ACC_H)
     const int nl = part * 64;
     const uint32_t xa_row = xa + (uint32_t)(part * SUB) + (uint32_t)(row * 128);
     int64_t it = 0;
+    int tr_n = (warp == 2 && lane == 0) ? 0 : 1000000; (void)tr_n;
     for (int64_t tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int64_t m_tile = tile * 2 + rank;
       const RowMap rm{m_tile * BM, q * 32, 0, 0};
-      // ---------------- LayerNorm1: x1 = LN(acc + bo + x) -> parked in ACC_O (fp32) and written to XA (fp16 A operand)
+      // ---------------- LayerNorm1: x1 = LN(acc + bo + x), acc in ACC_H -> parked in ACC_O (fp32; this warp's own lanes and
+      // columns, which it has finished reading in LayerNorm2 of the previous tile) and written to XA (fp16 A operand)
       {
         float s1 = 0.f, s2 = 0.f;
-        uint4 rres[4];
-        unit_load(reinterpret_cast<const char*>(p.x_in), (int64_t)DM * 4, rm, p.M, (int64_t)nl * 4, lane, rres);
+        uint4 rres[NCH][4];                                  // the whole 32 x 64 fp32 residual block of this warp, in flight before the wait
+#pragma unroll
+        for (int u = 0; u < NCH; ++u)
+          unit_load(reinterpret_cast<const char*>(p.x_in), (int64_t)DM * 4, rm, p.M, (int64_t)(nl + u * CW) * 4, lane, rres[u]);
         mbar_wait(bar(B_OFULL), (uint32_t)(it & 1));
         tc_fence_after();
+        TL_TRACE(1, 1);
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
-          unit_to_smem(stg, lane, rres);
+          unit_to_smem(stg, lane, rres[u]);
           __syncwarp();
-          if (u + 1 < NCH) unit_load(reinterpret_cast<const char*>(p.x_in), (int64_t)DM * 4, rm, p.M, (int64_t)(nl + (u + 1) * CW) * 4, lane, rres);
           uint32_t raw[CW];
-          tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
+          tmem_ld16_issue(t_p + (uint32_t)(u * CW), raw);
           tmem_ld16_wait(raw);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -260,7 +303,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
             raw[i * 4] = __float_as_uint(v0); raw[i * 4 + 1] = __float_as_uint(v1);
             raw[i * 4 + 2] = __float_as_uint(v2); raw[i * 4 + 3] = __float_as_uint(v3);
           }
-          tmem_st16(t_o + (uint32_t)(u * CW), raw);
+          tmem_st16(t_p + (uint32_t)(u * CW), raw);        // pre-norm sum parked in place (ACC_H)
           __syncwarp();
         }
         tmem_st_wait();
@@ -281,7 +324,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           uint32_t raw[CW];
-          tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
+          tmem_ld16_issue(t_p + (uint32_t)(u * CW), raw);
           tmem_ld16_wait(raw);
           float y[CW];
 #pragma unroll
@@ -310,26 +353,36 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar(B_X1));
+        TL_TRACE(1, 2);
       }
       // ---------------- hidden chunks: relu(ACC_H + b1) -> fp16 -> HB (A operand of FFN2)
+      if (tile + tile_step < total_tiles) {                  // the residual rows LayerNorm1 of the NEXT tile reads: pull them into L2 now
+        const int64_t nr = ((tile + tile_step) * 2 + rank) * BM + row;
+        if (nr < p.M) {
+          const char* a = reinterpret_cast<const char*>(p.x_in + nr * DM + nl);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+        }
+      }
       for (int i = 0; i < p.n_chunks; ++i) {
         const int b = i & 1;
         const int64_t seq = it * HC + (i >> 1);              // completions of this buffer's barriers before this chunk
         mbar_wait(bar(B_HFULL + b), (uint32_t)(seq & 1));
         tc_fence_after();
+        TL_TRACE(1, 200 + i);
         uint32_t r0[CW], r1[CW];
         tmem_ld16_issue(t_h + (uint32_t)(b * HCOLS), r0);
         tmem_ld16_issue(t_h + (uint32_t)(b * HCOLS + CW), r1);
         tmem_ld16_wait(r0);
         tmem_ld16_wait(r1);
-        const float* b1 = p.b1 + i * HCOLS + part * 32;
+        const float* b1 = s_par + 6 * DM + i * HCOLS + part * 32;
         uint4 o[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const uint32_t* src = c < 2 ? r0 : r1;
           const int off = (c & 1) * 8;
-          const float4 ba = __ldg(reinterpret_cast<const float4*>(b1 + c * 8));
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + c * 8 + 4));
+          const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
           __half2* hh = reinterpret_cast<__half2*>(&o[c]);
           hh[0] = __floats2half2_rn(fmaxf(__uint_as_float(src[off]) + ba.x, 0.f), fmaxf(__uint_as_float(src[off + 1]) + ba.y, 0.f));
           hh[1] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(src[off + 3]) + ba.w, 0.f));
@@ -344,12 +397,14 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(bar(B_HREADY + b));
+        TL_TRACE(1, 300 + i);
       }
       // ---------------- LayerNorm2: x = LN(acc + b2) (acc already holds x1 + FFN) -> fp32 stream + fp16 copy
       {
         float s1 = 0.f, s2 = 0.f;
         mbar_wait(bar(B_O2FULL), (uint32_t)(it & 1));
         tc_fence_after();
+        TL_TRACE(1, 9);
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           uint32_t raw[CW];
@@ -367,7 +422,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           tmem_st16(t_o + (uint32_t)(u * CW), raw);
         }
         tmem_st_wait();
-        const uint32_t red1 = red0 + (uint32_t)(EPI_WARPS * 32 * 8);
+        const uint32_t red1 = red0;
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red1 + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
         float S1 = 0.f, S2 = 0.f;
@@ -388,11 +443,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           uint32_t raw[CW];
           tmem_ld16_issue(t_o + (uint32_t)(u * CW), raw);
           tmem_ld16_wait(raw);
-          if (u == NCH - 1) {                                 // last TMEM read of the tile: ACC_O may be overwritten
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(bar(B_OFREE));
-          }
+          if (u == NCH - 1) tc_fence_before();                // last TMEM read of the tile (ordered before this warp's next barrier arrive)
           float y[CW];
 #pragma unroll
           for (int i = 0; i < CW; i += 4) {
@@ -442,7 +493,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 
-bool tlayer_tail_supported(int64_t M, int ffn_dim) { return M > 128 && ffn_dim >= 256 && ffn_dim % 256 == 0; }
+bool tlayer_tail_supported(int64_t M, int ffn_dim) { return M > 128 && ffn_dim >= 256 && ffn_dim % 256 == 0 && ffn_dim <= MAX_FFN; }
 
 cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t, cudaStream_t s, char* err, int errlen) {
   if (t.M <= 0) return cudaSuccess;
@@ -450,7 +501,7 @@ cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t
     snprintf(err, errlen, "tlayer_tail: %s (M=%lld ffn=%d)", msg, (long long)t.M, t.ffn_dim);
     return cudaErrorInvalidValue;
   };
-  if (!tlayer_tail_supported(t.M, t.ffn_dim)) return bad("needs more than 128 rows and ffn_dim a multiple of 256");
+  if (!tlayer_tail_supported(t.M, t.ffn_dim)) return bad("needs more than 128 rows and ffn_dim a multiple of 256, at most 1024");
   if (!t.att16 || !t.x32 || !t.x16 || !t.Wo16 || !t.W1_16 || !t.W2_16 || !t.bo || !t.b1 || !t.b2 || !t.ln1_g || !t.ln1_b || !t.ln2_g || !t.ln2_b)
     return bad("NULL argument");
   if ((reinterpret_cast<uintptr_t>(t.att16) | reinterpret_cast<uintptr_t>(t.x32) | reinterpret_cast<uintptr_t>(t.x16) |
@@ -503,3 +554,10 @@ cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k_tlayer_tail, m_att, m_wo, m_w1, m_w2, p);
 }
+
+#ifdef TAG_EXPERIMENTS
+extern "C" int tag_exp_set_tlayer_trace(void* dev_buf) {        // experiments build only (tools/tl_trace.py); 3 roles x 4096 int64
+  long long* p = reinterpret_cast<long long*>(dev_buf);
+  return (int)cudaMemcpyToSymbol(g_tl_trace, &p, sizeof(p));
+}
+#endif
