@@ -336,11 +336,20 @@ def other_configs(args, pkg, torch, dist, dev, rank, world, model, scorer, stats
         dist.all_gather(allc, cen3)
         identical = all(torch.equal(allc[0], c) for c in allc)
         assert identical, "ranks disagree on the all-reduced centroids"
-    ar_us = 1000.0 * statistics.median(a.elapsed_time(b) for a, b in ar_ev[-steps:]) if world > 1 else None
+    ar_us = ar_wait_us = None
+    if world > 1:
+        # events around the collective on the compute stream: a rank that arrives early also waits for the slowest rank in
+        # there, so the MIN over ranks is the collective's own latency (seen by the last rank to arrive), the MAX the skew
+        t = torch.tensor([1000.0 * statistics.median(a.elapsed_time(b) for a, b in ar_ev[-steps:])], device=dev, dtype=torch.float64)
+        tmin, tmax = t.clone(), t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ar_us, ar_wait_us = float(tmin.item()), float(tmax.item())
     out["config3"] = entry(ms, n3, "clips", wpv * GFLOP_PER_WINDOW,
                            f"centroid build: {n3} clips x {args.frames} frames per GPU ({n3 * wpv} windows; 8 GPUs = BASELINE's 100k clips), K1 + encoder + K3, "
                            "NCCL all-reduce of the packed [10,257] sums||counts + finalize inside the timed region")
-    out["config3"].update({"allreduce_us": ar_us, "allreduce_bytes": 10 * 257 * 4, "centroids_identical_on_all_ranks": identical})
+    out["config3"].update({"allreduce_us": ar_us, "allreduce_incl_rank_skew_us_max": ar_wait_us, "allreduce_bytes": 10 * 257 * 4,
+                           "centroids_identical_on_all_ranks": identical})
     del v3, dv3
 
     # ---- config 5: 4096 clips x 32 frames, encoder forward + TCL similarity matrix (per-rank batch, no all-gather: SURVEY.md §8e)

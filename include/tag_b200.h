@@ -209,6 +209,10 @@ int tag_debug_gemm_tc(tag_handle* h, const void* A, int32_t lda, const void* W, 
                       void* C16, float* C32, int32_t act, const float* gn_gamma, const float* gn_beta,
                       const float* ln_gamma, const float* ln_beta, void* stream);
 
+/* test hook: fill every workspace buffer of the handle (activations, token stream, fp16 operand tables, staging rows) with
+ * 0xFF bytes = NaN in fp16 and fp32, so that a kernel that reads something it did not write this call shows up as NaN. */
+int tag_debug_poison_workspace(tag_handle* h, void* stream);
+
 /* the fused tail of one transformer layer (model.py:145, post-norm): x32 <- LN2(x1 + relu(x1 W1^T + b1) W2^T + b2) with
  * x1 = LN1(x32 + att16 Wo^T + bo), in place, plus the fp16 copy x16; M > 128 rows, ffn_dim a multiple of 256; weights fp16
  * [out, in] row-major. This is the kernel tag_encode* runs once per layer in tensor-core mode. */

@@ -401,3 +401,48 @@ def test_tlayer_tail_fused(M, F):
     assert lib.tag_debug_tlayer_tail(h, att.data_ptr(), Xio.data_ptr(), X16.data_ptr(), 100, F, Wo.data_ptr(), W1.data_ptr(), W2.data_ptr(),
                                      bo.data_ptr(), b1.data_ptr(), b2.data_ptr(), g1.data_ptr(), be1.data_ptr(), g2.data_ptr(),
                                      be2.data_ptr(), torch.cuda.current_stream().cuda_stream) != 0
+
+
+@pytest.mark.parametrize("precision", ["fp16_tc", "fp32"])
+def test_workspace_poisoning_changes_nothing(precision):
+    """Every workspace buffer (activations, token stream, fp16 operand table incl. its pad columns, zero-motion rows) filled
+    with NaN bytes before the call: scores must come out bit-identical to a run on the freshly allocated (zeroed) workspace —
+    no kernel reads what an earlier kernel of the same call did not write. Both the window path and the frame-table path,
+    ragged and uniform batches, and the drop-in forward."""
+    g = golden_case("m5_t32")
+    lib = _lib.load()
+    model = _model(g, precision, max_windows=24)
+    scorer = tb.TagScorer(model, g.stats(), clip_len=g.clip_len, stride=g.stride, device=DEV)
+    cen = torch.from_numpy(g.npz["centroids"]).to(DEV)
+    uni = tb.make_videos(9, 64, seed=31)
+    batches = [scorer.to_device(g.gen.to(DEV)), scorer.to_device(uni.to(DEV))]
+    x = torch.randn(5, 32, model.feat_dim, device=DEV)
+    clean = [tuple(t.clone() for t in scorer.score(dv, cen)) for dv in batches]
+    fwd_clean = tuple(t.clone() for t in model(x))
+    h = model.handle(torch.device(DEV), g.clip_len)
+    s = torch.cuda.current_stream().cuda_stream
+    for rnd in range(2):
+        for dv, want in zip(batches, clean):
+            _lib.check(h, lib.tag_debug_poison_workspace(h, s), "tag_debug_poison_workspace")
+            ac, tc = scorer.score(dv, cen)
+            assert torch.equal(ac, want[0]) and torch.equal(tc, want[1])
+        _lib.check(h, lib.tag_debug_poison_workspace(h, s), "tag_debug_poison_workspace")
+        got = model(x)
+        for a, b in zip(got, fwd_clean):
+            assert torch.equal(a, b)
+
+
+def test_score_stream_empty_batches_and_oversized_videos():
+    """a batch with no videos yields an empty result in its place; a video with more windows than max_windows still
+    scores (one oversized block)."""
+    g = golden_case("m5_t32")
+    model = _model(g, "fp16_tc", max_windows=4)
+    scorer = tb.TagScorer(model, g.stats(), clip_len=g.clip_len, stride=g.stride, device=DEV)
+    cen = torch.from_numpy(g.npz["centroids"]).to(DEV)
+    full = g.gen.pin()                                  # 64-frame videos have 5 windows > max_windows = 4
+    empty = g.gen.slice(0, 0)
+    out = list(scorer.score_stream(iter([empty, full, empty, g.gen.slice(2, 5).pin(), empty]), cen))
+    assert [o[0].numel() for o in out] == [0, g.gen.n_videos, 0, 3, 0]
+    want = scorer.score(scorer.to_device(g.gen.to(DEV)), cen)
+    assert torch.allclose(out[1][0], want[0].cpu(), rtol=5e-4, atol=0, equal_nan=True)
+    assert torch.allclose(out[3][1], want[1].cpu()[2:5], rtol=5e-4, atol=0)

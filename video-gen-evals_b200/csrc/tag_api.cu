@@ -1147,6 +1147,31 @@ int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x1
   return TAG_OK;
 }
 
+int tag_debug_poison_workspace(tag_handle* h, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  if (!h->finalized) return fail(h, TAG_ERR_STATE, "tag_finalize_weights has not been called");
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool tc = h->cfg.precision == TAG_PRECISION_FP16_TC;
+  const size_t es = tc ? sizeof(__half) : sizeof(float);
+  const size_t R = (size_t)h->cfg.max_windows * h->cfg.max_T, R2 = (size_t)h->cfg.max_windows * (h->cfg.max_T + 1);
+  const size_t F = (size_t)h->cfg.ffn_dim;
+  auto poison = [&](void* p, size_t bytes) { return p == nullptr ? cudaSuccess : cudaMemsetAsync(p, 0xFF, bytes, s); };   // 0xFF.. = NaN (fp16 and fp32)
+  void* act[] = {h->bufH, h->bufY1, h->bufY2, h->mix, h->fusedA, h->fusedB};
+  for (void* p : act) CUDA_TRY(h, poison(p, R * kD * es));
+  for (int e = 0; e < 2 * h->M; ++e) CUDA_TRY(h, poison(h->P[e], R * kD * es));
+  CUDA_TRY(h, poison(h->X, R2 * kD * sizeof(float)));
+  CUDA_TRY(h, poison(h->TMP, R2 * kD * sizeof(float)));
+  CUDA_TRY(h, poison(h->QKV, R2 * 3 * kD * es));
+  CUDA_TRY(h, poison(h->ATT, R2 * kD * es));
+  CUDA_TRY(h, poison(h->FF, R2 * F * es));
+  CUDA_TRY(h, poison(h->X16, R2 * kD * es));
+  CUDA_TRY(h, poison(h->feats16, R * h->D16 * sizeof(__half)));
+  CUDA_TRY(h, poison(h->feats, R * h->D * sizeof(float)));
+  CUDA_TRY(h, poison(h->row0, (size_t)h->M * kD * sizeof(float)));
+  return TAG_OK;
+}
+
 int64_t tag_launch_count(const tag_handle* h) { return h ? h->launches : 0; }
 
 int tag_set_profiling(tag_handle* h, int32_t on) {
