@@ -93,6 +93,10 @@ int tag_abi_version(void);
  * modality NAME replaced by its index: "state_enc.0.blocks..."); data may be HOST or DEVICE. */
 int tag_load_weight(tag_handle* h, const char* key, const float* data, const int64_t* shape, int32_t ndim);
 int tag_finalize_weights(tag_handle* h);
+/* new parameter VALUES for a finalized handle (same architecture): tag_reload_weights_begin, then tag_load_weight for every
+ * tensor, then tag_finalize_weights again — only the packed weights are rebuilt, the workspace (GBs) is kept. This is what a
+ * training loop calls between optimiser steps before the next embedding pass (train.py:488-509). */
+int tag_reload_weights_begin(tag_handle* h);
 
 /* --- K1 feature fuse: WindowDataset._try_one compute part (utils.py:366-381, :396-404,
  *     :455-514): slice/pad, raw flatten, per-window deltas, z-score, concat [raw || diff].

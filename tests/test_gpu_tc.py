@@ -446,3 +446,28 @@ def test_score_stream_empty_batches_and_oversized_videos():
     want = scorer.score(scorer.to_device(g.gen.to(DEV)), cen)
     assert torch.allclose(out[1][0], want[0].cpu(), rtol=5e-4, atol=0, equal_nan=True)
     assert torch.allclose(out[3][1], want[1].cpu()[2:5], rtol=5e-4, atol=0)
+
+
+@pytest.mark.parametrize("precision", ["fp16_tc", "fp32"])
+def test_weight_reload_keeps_the_handle(precision):
+    """New parameter values (an optimiser step in the reference's training loop, train.py:502-505) re-pack the weights into the
+    existing native handle — same handle pointer, same workspace — and give exactly what a freshly built model gives."""
+    g = golden_case("m5_t32")
+    x = torch.randn(6, 32, sum(g.dims_raw.values()) + sum(g.dims_diff.values()), device=DEV)
+    model = _model(g, precision, max_windows=8)
+    out0 = tuple(t.clone() for t in model(x))
+    h0 = model._h.value
+    sd2 = tb.make_state_dict(g.dims_raw, g.dims_diff, seed=5)
+    model.load_state_dict(sd2)                          # in-place copy_: parameter versions change, storage does not
+    out1 = model(x)
+    assert model._h.value == h0                         # re-packed, not re-created
+    fresh = tb.HumanActionScorer(g.dims_raw, g.dims_diff, precision=precision, max_windows=8)
+    fresh.load_state_dict(sd2)
+    fresh.to(DEV).eval()
+    want = fresh(x)
+    for a, b in zip(out1, want):
+        assert torch.equal(a, b)
+    assert not torch.equal(out1[0], out0[0])
+    model.load_state_dict(g.sd)
+    for a, b in zip(model(x), out0):
+        assert torch.equal(a, b)

@@ -48,6 +48,7 @@ SIGNATURES = {
     "tag_abi_version": (C.c_int, []),
     "tag_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(_I64), _I32]),
     "tag_finalize_weights": (C.c_int, [_P]),
+    "tag_reload_weights_begin": (C.c_int, [_P]),
     "tag_feature_fuse": (C.c_int, [_P, C.POINTER(tag_videos), _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
     "tag_encode": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
     "tag_set_fusion_attn_out": (C.c_int, [_P, _P]),

@@ -54,7 +54,10 @@ struct tag_handle {
 
   std::map<std::string, std::vector<float>> staged;
   std::map<std::string, std::vector<int64_t>> staged_shape;
-  std::vector<void*> allocs;
+  std::vector<void*> allocs;        // workspace and tables (live as long as the handle)
+  std::vector<void*> w_allocs;      // packed weights (replaced by tag_reload_weights_begin + load + finalize)
+  bool packing_weights = false;     // dev_alloc sink selector
+  bool reloading = false;
 
   EncWeights state[TAG_MAX_MODALITIES], motion[TAG_MAX_MODALITIES];
   std::vector<LayerWeights> layers;
@@ -117,7 +120,7 @@ int dev_alloc(tag_handle* h, T** p, size_t n) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
   if (e != cudaSuccess) return fail(h, TAG_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
-  h->allocs.push_back(q);
+  (h->packing_weights ? h->w_allocs : h->allocs).push_back(q);
   *p = reinterpret_cast<T*>(q);
   return TAG_OK;
 }
@@ -603,6 +606,7 @@ void tag_destroy(tag_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->w_allocs) cudaFree(p);
   if (h->k3_scratch) cudaFree(h->k3_scratch);
   if (h->tcl_A) cudaFree(h->tcl_A);
   if (h->tcl_W) cudaFree(h->tcl_W);
@@ -626,16 +630,34 @@ int tag_load_weight(tag_handle* h, const char* key, const float* data, const int
   return TAG_OK;
 }
 
+int tag_reload_weights_begin(tag_handle* h) {
+  if (!h) return TAG_ERR_INVALID;
+  if (!h->finalized) return fail(h, TAG_ERR_STATE, "tag_reload_weights_begin: the handle has no finalized weights yet");
+  h->finalized = false;
+  h->reloading = true;
+  return TAG_OK;
+}
+
 int tag_finalize_weights(tag_handle* h) {
   if (!h) return TAG_ERR_INVALID;
   if (h->finalized) return fail(h, TAG_ERR_STATE, "weights already finalized");
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   const bool tc = h->cfg.precision == TAG_PRECISION_FP16_TC;
   int rc;
-  if (tc) {
+  if (h->reloading) {
+    // new parameter values for an existing handle (a training loop between optimiser steps, BASELINE config 5): only the
+    // packed weights are rebuilt; workspace, tensor-core context and tables stay
+    CUDA_TRY(h, cudaDeviceSynchronize());          // launches that still read the old weights
+    for (void* p : h->w_allocs) cudaFree(p);
+    h->w_allocs.clear();
+    for (int m = 0; m < TAG_MAX_MODALITIES; ++m) { h->state[m] = EncWeights{}; h->motion[m] = EncWeights{}; }
+    h->layers.clear();
+  } else if (tc && !h->tc) {
     h->tc = tc_context_create(h->cfg.device, h->err, 512);
     if (!h->tc) return TAG_ERR_CUDA;
   }
+  h->packing_weights = true;
+  struct Unset { tag_handle* h; ~Unset() { h->packing_weights = false; } } unset{h};
   for (int m = 0; m < h->M; ++m) {
     rc = pack_encoder(h, "state_enc." + std::to_string(m), h->cfg.raw_dims[m], &h->state[m]); if (rc) return rc;
     if (h->cfg.diff_dims[m] > 0) {
@@ -743,6 +765,12 @@ int tag_finalize_weights(tag_handle* h) {
   }
   h->staged.clear();
   h->staged_shape.clear();
+  h->packing_weights = false;
+  if (h->reloading) {
+    h->reloading = false;
+    h->finalized = true;
+    return TAG_OK;
+  }
 
   // ---- workspace
   const size_t es = tc ? sizeof(__half) : sizeof(float);

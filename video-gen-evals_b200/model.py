@@ -181,9 +181,21 @@ class HumanActionScorer(nn.Module):
             raise _lib.TagError("HumanActionScorer runs only on a CUDA (sm_100a) device; there is no CPU path")
         dev_index = device.index if device.index is not None else torch.cuda.current_device()
         sig = self._signature()
-        if self._h is not None and self._h_key[0] == dev_index and self._h_key[1] >= T_frames and \
-                self._h_key[2:] == (self.precision, self.max_windows) and self._w_sig == sig:
+        same_shape = self._h is not None and self._h_key[0] == dev_index and self._h_key[1] >= T_frames and \
+            self._h_key[2:] == (self.precision, self.max_windows)
+        if same_shape and self._w_sig == sig:
             return self._h
+        if same_shape:
+            # parameter values changed (e.g. an optimiser step): re-pack the weights into the existing handle, keep its workspace
+            h, max_T = self._h, self._h_key[1]
+            _lib.check(h, lib.tag_reload_weights_begin(h), "tag_reload_weights_begin")
+            try:
+                self._load_all(lib, h, max_T)
+            except Exception:
+                self._release()
+                raise
+            self._w_sig = sig
+            return h
         self._release()
         max_T = max(32, int(T_frames))
         cfg = _lib.tag_config()
@@ -200,23 +212,27 @@ class HumanActionScorer(nn.Module):
         h = C.c_void_p()
         _lib.check(None, lib.tag_create(C.byref(h), C.byref(cfg)), "tag_create")
         try:
-            idx = {m: str(i) for i, m in enumerate(self.modalities)}
-            for key, t in self.state_dict().items():
-                parts = key.split(".")
-                if parts[0] in ("state_enc", "motion_enc"):
-                    parts[1] = idx[parts[1]]
-                if key == "pos_enc.pe":
-                    t = t[:, :max_T + 1, :]
-                t = t.detach().to(torch.float32).contiguous()
-                shape = (C.c_int64 * t.dim())(*t.shape)
-                _lib.check(h, lib.tag_load_weight(h, ".".join(parts).encode(), t.data_ptr(), shape, t.dim()),
-                           f"tag_load_weight({key})")
-            _lib.check(h, lib.tag_finalize_weights(h), "tag_finalize_weights")
+            self._load_all(lib, h, max_T)
         except Exception:
             lib.tag_destroy(h)
             raise
         self._h, self._h_key, self._w_sig = h, (dev_index, max_T, self.precision, self.max_windows), sig
         return h
+
+    def _load_all(self, lib, h, max_T: int):
+        """every state_dict tensor -> tag_load_weight (modality names become indices in the keys), then finalize"""
+        idx = {m: str(i) for i, m in enumerate(self.modalities)}
+        for key, t in self.state_dict().items():
+            parts = key.split(".")
+            if parts[0] in ("state_enc", "motion_enc"):
+                parts[1] = idx[parts[1]]
+            if key == "pos_enc.pe":
+                t = t[:, :max_T + 1, :]
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(h, lib.tag_load_weight(h, ".".join(parts).encode(), t.data_ptr(), shape, t.dim()),
+                       f"tag_load_weight({key})")
+        _lib.check(h, lib.tag_finalize_weights(h), "tag_finalize_weights")
 
     # ------------------------------------------------------------------ reference forward contract
     def forward(self, x: torch.Tensor, modality_mask=None):
