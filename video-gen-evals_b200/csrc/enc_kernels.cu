@@ -814,30 +814,42 @@ __global__ void __launch_bounds__(256) k_layernorm(const float* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------- output head: one warp per window
-// Rows are taken four at a time: the four 1 KB loads are in flight together and the warp-shuffle chains of the four row norms
-// (then of the four consecutive-frame distances) are interleaved, so the kernel streams instead of waiting on one
-// load -> shuffle -> sqrt chain per token (round 1: 3.0 TB/s; the token stream is read once, 1 KB per token).
+// Rows are taken four at a time, and the NEXT four are loaded before these four are processed: 8 KB per warp in flight, the
+// warp-shuffle chains of the four row norms (then of the four consecutive-frame distances) interleaved, so the kernel streams
+// instead of waiting on one load -> shuffle -> sqrt chain per token (round 1: 3.0 TB/s; the token stream is read once, 1 KB
+// per token). 128-thread CTAs (4 windows) keep the last wave short.
 template <bool NORMALIZE>
-__global__ void __launch_bounds__(256) k_finalize(const float* __restrict__ tokens, int64_t n_windows, int S,
+__global__ void __launch_bounds__(128) k_finalize(const float* __restrict__ tokens, int64_t n_windows, int S,
                                                   float* __restrict__ seq, float* __restrict__ frame_embeds,
                                                   float* __restrict__ tokens_out, float* __restrict__ tc_window) {
-  const int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t n = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= n_windows) return;
   constexpr int U = 4;
+  const float* base = tokens + n * S * kD + lane * 8;
   float prev[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) prev[k] = 0.f;
   float tsum = 0.f;
+  float nxt[U][8];                                             // the NEXT four rows are already in flight while these four are processed
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < S) Row8<float>::load(base + (int64_t)u * kD, nxt[u]);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) nxt[u][k] = 0.f;
+    }
+  }
   for (int s0 = 0; s0 < S; s0 += U) {
     float v[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (s0 + u < S) Row8<float>::load(tokens + (n * S + s0 + u) * kD + lane * 8, v[u]);
-      else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
-      }
+      for (int k = 0; k < 8; ++k) v[u][k] = nxt[u][k];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (s0 + U + u < S) Row8<float>::load(base + (int64_t)(s0 + U + u) * kD, nxt[u]);
     }
     if (tokens_out != nullptr) {
 #pragma unroll
@@ -999,13 +1011,13 @@ template cudaError_t launch_layernorm<__half>(const float*, const float*, const 
 cudaError_t launch_finalize(const float* tokens, int64_t n_windows, int S, float* seq, float* frame_embeds,
                             float* tokens_out, float* tc_window, cudaStream_t s) {
   if (n_windows <= 0) return cudaSuccess;
-  k_finalize<true><<<(unsigned)((n_windows + 7) / 8), 256, 0, s>>>(tokens, n_windows, S, seq, frame_embeds, tokens_out, tc_window);
+  k_finalize<true><<<(unsigned)((n_windows + 3) / 4), 128, 0, s>>>(tokens, n_windows, S, seq, frame_embeds, tokens_out, tc_window);
   return cudaGetLastError();
 }
 
 // eval.py:218-224 on already-normalised frame embeddings [N, S, 256] (S = T+1, row 0 = CLS)
 cudaError_t launch_window_tc(const float* frame_embeds, int64_t n_windows, int S, float* tc_window, cudaStream_t s) {
   if (n_windows <= 0) return cudaSuccess;
-  k_finalize<false><<<(unsigned)((n_windows + 7) / 8), 256, 0, s>>>(frame_embeds, n_windows, S, nullptr, nullptr, nullptr, tc_window);
+  k_finalize<false><<<(unsigned)((n_windows + 3) / 4), 128, 0, s>>>(frame_embeds, n_windows, S, nullptr, nullptr, nullptr, tc_window);
   return cudaGetLastError();
 }
