@@ -35,7 +35,7 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{k}` | {v[0]} | {v[1] / 1e6:.3f} | {v[1] / tot * 100:.1f} % | {v[1] / v[0] / 1e3:.1f} |")
 print(f"\nconv1 launches (the `<0,1>` launch right before each `<1,1>`): {len(conv1)}, {sum(conv1) / 1e6:.2f} ms = {sum(conv1) / tot * 100:.1f} %; "
       f"dilated-conv GEMMs together {(sum(conv1) + gn) / 1e6:.2f} ms = **{(sum(conv1) + gn) / tot * 100:.1f} % of the step**.")
-gem = sum(v[1] for k, v in agg.items() if k.startswith("k_gemm_tc")) - sum(conv1) - gn
+gem = sum(v[1] for k, v in agg.items() if k.startswith("k_gemm_tc") or k.startswith("k_tlayer_tail")) - sum(conv1) - gn
 k1t = sum(v[1] for k, v in agg.items() if "feature_fuse" in k)
 oth = tot - gem - sum(conv1) - gn - k1t
 print(f"other GEMMs {gem / tot * 100:.1f} %, K1 {k1t / tot * 100:.1f} %, other kernels {oth / tot * 100:.1f} %.")
