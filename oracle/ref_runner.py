@@ -2,9 +2,10 @@
 
 The reference (XThomasBU/video-gen-evals) is pure Python: nothing to compile. `build_ref()` — called by
 `__graft_entry__.build()` in the build container, where /root/reference exists — places the reference's own
-`model.py`, `utils.py`, `eval.py`, `losses.py`, `process_scores.py` (+ the human-score table) into the git-ignored `oracle/_ref/`
-(not gpurun-ignored, so it travels to the GPU box next to the built .so). Nothing under `oracle/_ref/` is
-ever committed, imported by the product package, or modified.
+`model.py`, `utils.py`, `eval.py`, `losses.py`, `process_scores.py` (+ the human-score table) as ONE archive into the git-ignored
+`oracle/_ref/` (not gpurun-ignored, so it travels to the GPU box next to the built .so); `load_ref()` unpacks it into a scratch
+directory outside the repository and imports from there. Nothing under `oracle/_ref/` is ever committed, imported by the
+product package, or modified.
 
 Users (and only these): `tests/`, `bench.py --impl reference` / `cpu_baseline`. `load_ref()` returns None when
 `oracle/_ref/` is absent (a fresh clone without the reference): callers then fall back to the oracle port
@@ -29,23 +30,62 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+ARCHIVE = os.path.join(REF_DIR, "reference_modules.tar.gz")
 FILES = ("model.py", "utils.py", "eval.py", "losses.py", "process_scores.py", "TAG_final_human_scores.json")
-HUMAN_SCORES = os.path.join(REF_DIR, "TAG_final_human_scores.json")     # 300 TAG-Bench file names + human MOS (eval.py:297-347)
 
 
 def build_ref(src: Optional[str] = None) -> Optional[str]:
-    """Copy the reference's scoring-path modules into oracle/_ref/ (byte-identical). No-op when the reference
-    is not present (GPU box: the directory arrived with the snapshot)."""
+    """Pack the reference's scoring-path modules, byte-identical, into ONE archive under the git-ignored oracle/_ref/
+    (it travels to the GPU box with the built .so; no loose copies of reference sources lie in the tree). No-op when the
+    reference is not present (GPU box: the archive arrived with the snapshot)."""
+    import tarfile
     src = src or os.environ.get("TAG_REFERENCE", "/root/reference")
     if not os.path.isdir(src):
-        return REF_DIR if os.path.isdir(REF_DIR) else None
+        return ARCHIVE if os.path.exists(ARCHIVE) else None
     os.makedirs(REF_DIR, exist_ok=True)
-    for f in FILES:
-        shutil.copyfile(os.path.join(src, f), os.path.join(REF_DIR, f))
-    return REF_DIR
+    for f in os.listdir(REF_DIR):                      # loose files of an earlier layout
+        if f != os.path.basename(ARCHIVE):
+            os.remove(os.path.join(REF_DIR, f))
+    tmp = ARCHIVE + ".tmp"
+    with tarfile.open(tmp, "w:gz") as tar:
+        for f in FILES:
+            tar.add(os.path.join(src, f), arcname=f)
+    os.replace(tmp, ARCHIVE)
+    return ARCHIVE
 
 
 _cached = None
+_unpacked = None
+
+
+def unpack_dir() -> Optional[str]:
+    """The archive extracted into a per-archive scratch directory (outside the repository), or None."""
+    global _unpacked
+    import hashlib
+    import tarfile
+    if _unpacked is not None:
+        return _unpacked
+    if not os.path.exists(ARCHIVE):
+        return None
+    with open(ARCHIVE, "rb") as f:
+        tag = hashlib.sha256(f.read()).hexdigest()[:16]
+    d = os.path.join(tempfile.gettempdir(), f"tag_reference_{tag}_{os.getuid()}")
+    if not all(os.path.exists(os.path.join(d, f)) for f in FILES):
+        tmp = tempfile.mkdtemp(prefix="tag_reference_unpack_")
+        with tarfile.open(ARCHIVE, "r:gz") as tar:
+            tar.extractall(tmp, filter="data")
+        try:
+            os.replace(tmp, d)
+        except OSError:                                # another process won the race
+            shutil.rmtree(tmp, ignore_errors=True)
+    _unpacked = d
+    return d
+
+
+def human_scores_path() -> Optional[str]:
+    """300 TAG-Bench file names + human MOS (eval.py:297-347), from the archive."""
+    d = unpack_dir()
+    return None if d is None else os.path.join(d, "TAG_final_human_scores.json")
 
 
 def load_ref():
@@ -53,15 +93,16 @@ def load_ref():
     global _cached
     if _cached is not None:
         return _cached
-    if not all(os.path.exists(os.path.join(REF_DIR, f)) for f in FILES):
+    d = unpack_dir()
+    if d is None:
         return None
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)          # the reference's modules import each other by bare name (eval.py:7, :16)
+    if d not in sys.path:
+        sys.path.insert(0, d)                # the reference's modules import each other by bare name (eval.py:7, :16)
     mods = {}
     for name in ("model", "utils", "eval", "losses", "process_scores"):
         m = importlib.import_module(name)
-        if os.path.dirname(os.path.abspath(m.__file__)) != REF_DIR:
-            raise ImportError(f"module '{name}' resolved to {m.__file__}, not to oracle/_ref")
+        if os.path.dirname(os.path.abspath(m.__file__)) != os.path.abspath(d):
+            raise ImportError(f"module '{name}' resolved to {m.__file__}, not to the unpacked reference")
         mods[name] = m
     _cached = SimpleNamespace(**mods)
     return _cached

@@ -33,7 +33,7 @@ class Bench300:
 
     def __init__(self):
         ref = REF
-        with open(RR.HUMAN_SCORES) as f:
+        with open(RR.human_scores_path()) as f:
             human = json.load(f)
         names = sorted(human)
         self.n = int(os.environ.get("TAG_TEST_BENCH_VIDEOS", "300"))
@@ -201,8 +201,8 @@ def test_reporting_parity_process_scores_and_spearman(bench300, tmp_path):
     print(f"process_scores tables (0-100 scale): max |ours - reference| = {worst:.3f}")
     assert worst < 0.25                                # 1e-3 relative on scores spread over a 0-100 range, two-decimal rounding
     for key in ("ac", "tc"):
-        r_ours, _, m1 = ref.eval.compute_spearman_correlation({k: v[key] for k, v in ours.items()}, RR.HUMAN_SCORES, key)
-        r_ref, _, m2 = ref.eval.compute_spearman_correlation({k: v[key] for k, v in theirs.items()}, RR.HUMAN_SCORES, key)
+        r_ours, _, m1 = ref.eval.compute_spearman_correlation({k: v[key] for k, v in ours.items()}, RR.human_scores_path(), key)
+        r_ref, _, m2 = ref.eval.compute_spearman_correlation({k: v[key] for k, v in theirs.items()}, RR.human_scores_path(), key)
         print(f"Spearman vs human {key}: ours {r_ours:.4f} reference {r_ref:.4f} ({len(m1)} matched)")
         assert len(m1) == len(m2) >= 0.7 * b.n and abs(r_ours - r_ref) < 5e-3     # eval.py:318-331 matches most, not all, names
 
