@@ -8,15 +8,15 @@
 //
 //   TMEM   cols   0..255  ACC_O : x1 (fp32, parked by the LayerNorm1 epilogue with tcgen05.st); FFN2 accumulates ON TOP of it
 //          cols 256..511  ACC_H : the out-proj accumulator of the NEXT tile (issued while LayerNorm2 of this tile still reads
-//                                 ACC_O), then two 128-column halves: the FFN1 accumulators of hidden chunks i and i+1
+//                                 ACC_O), then the FFN1 accumulator of one 256-column hidden chunk at a time
 //   SMEM   XA   64 KiB    x1 as the fp16 A operand of FFN1 (written by the LayerNorm1 epilogue in the 128B-swizzled K-major layout)
-//          HB   2 x 32 KiB relu(h) chunks (128 hidden columns) as the fp16 A operand of FFN2, double buffered
+//          HB   2 x 32 KiB the two 128-column halves of relu(h) of a chunk as the fp16 A operand of FFN2
 //          RING 10 x 8 KiB TMA granules: attention tile + Wo (out-proj), W1 row blocks, W2 column blocks
 //
 // The [rows x 1024] FFN hidden state, x1 and its fp16 copy never touch HBM: per layer pass the kernel reads attn (fp16) and x
 // (fp32) and writes x (fp32) and its fp16 copy — 1.27 GB for 412,500 tokens instead of 4.1 GB for the three launches it replaces.
-// Hidden chunks are software pipelined: while the tensor pipe runs FFN2 of chunk i-1 and FFN1 of chunk i+1, the epilogue
-// warps turn chunk i (TMEM -> +b1 -> ReLU -> fp16 -> SMEM) around.
+// Hidden chunks are software pipelined in halves: while the epilogue warps turn one 128-column half of chunk c around
+// (TMEM -> +b1 -> ReLU -> fp16 -> SMEM), the tensor pipe runs FFN2 of the half before it (see the issue order in the MMA role).
 //
 // Roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (leader CTA), warps 2..17 epilogue
 // (4 per TMEM lane quarter x 4 column groups). Barrier protocol in the comments of each role; every wait is bounded.
@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -39,7 +40,8 @@ constexpr int SUB = BM * BK * 2;                 // 16 KiB: one [128 x 64] fp16 
 constexpr int UNIT = SUB / 2;                    // ring granule: 8 KiB (a W1 block); attention / Wo / W2 blocks take two
 constexpr int NS = 10;                           // ring granules (80 KiB). Two-granule loads always start on an even granule
                                                  // (single-granule loads come in fours), so they never straddle the wrap
-constexpr int HCOLS = 128;                       // hidden columns per chunk
+constexpr int HCOLS = 128;                       // hidden columns per hand-over (half a chunk)
+constexpr int WCOLS = 256;                       // hidden columns per FFN1 chunk (one N = 256 accumulator)
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int CW = 16;
@@ -55,16 +57,15 @@ static_assert(EPI_WARPS * STG_WARP_BYTES <= 4 * SUB, "the epilogue staging tiles
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t IDESC_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // f16 x f16 -> f32, M = 256 (pair)
-constexpr uint32_t IDESC_N128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 // barrier slots (8 B each)
 constexpr int B_RFULL = 0, B_REMPTY = NS, B_OFULL = 2 * NS, B_X1 = 2 * NS + 1, B_HFULL = 2 * NS + 2, B_HREADY = 2 * NS + 4,
-              B_HBFREE = 2 * NS + 6, B_O2FULL = 2 * NS + 8, B_OFREE = 2 * NS + 9, B_COUNT = 2 * NS + 10;
+              B_HBFREE = 2 * NS + 6, B_O2FULL = 2 * NS + 8, B_COUNT = 2 * NS + 10;
 
 struct TlParams {
   int64_t M;              // token rows
   int64_t m_tiles;
-  int n_chunks;           // ffn_dim / 128 (even)
+  int n_chunks;           // ffn_dim / 256
   const float* x_in;      // [M,256] fp32 residual stream (read)
   float* x_out;           // [M,256] fp32 (written; may alias x_in: a tile reads its rows before it writes them)
   __half* x16_out;        // [M,256] fp16 copy of x_out
@@ -100,20 +101,20 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HC = p.n_chunks >> 1;               // completions per tile of every per-buffer barrier
 
   for (int i = threadIdx.x; i < DM; i += THREADS) {
     s_par[i] = __ldg(p.bo + i); s_par[DM + i] = __ldg(p.b2 + i);
     s_par[2 * DM + i] = __ldg(p.ln1_g + i); s_par[3 * DM + i] = __ldg(p.ln1_b + i);
     s_par[4 * DM + i] = __ldg(p.ln2_g + i); s_par[5 * DM + i] = __ldg(p.ln2_b + i);
   }
-  for (int i = threadIdx.x; i < p.n_chunks * HCOLS; i += THREADS) s_par[6 * DM + i] = __ldg(p.b1 + i);   // a global load per chunk sat on the
+  for (int i = threadIdx.x; i < p.n_chunks * WCOLS; i += THREADS) s_par[6 * DM + i] = __ldg(p.b1 + i);   // a global load per chunk sat on the
                                                                                                        // chunk turn-around path (ncu: 55 % of it)
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(bar(B_RFULL + s), 1); mbar_init(bar(B_REMPTY + s), 1); }
     mbar_init(bar(B_OFULL), 1);
     mbar_init(bar(B_X1), EPI_WARPS * 2);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(B_HFULL + b), 1); mbar_init(bar(B_HREADY + b), EPI_WARPS * 2); mbar_init(bar(B_HBFREE + b), 1); }
+    mbar_init(bar(B_HFULL), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(B_HREADY + b), EPI_WARPS * 2); mbar_init(bar(B_HBFREE + b), 1); }
     mbar_init(bar(B_O2FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -153,25 +154,29 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           tma_load_2d_pair(d, &map_wo, bar(B_RFULL + slot), kb * BK, (int)rank * (DM / 2));
           advance(2);
         }
-        auto load_f1 = [&](int j) {                        // W1 rows of hidden chunk j: 64 per CTA
+        auto load_f1 = [&](int c) {                        // W1 rows of wide hidden chunk c (256 hidden columns): 128 per CTA
           for (int kb = 0; kb < DM / BK; ++kb) {
-            const uint32_t d = acquire(1);
-            tma_load_2d_pair(d, &map_w1, bar(B_RFULL + slot), kb * BK, j * HCOLS + (int)rank * (HCOLS / 2));
-            TL_TRACE(2, 200 + j * 4 + kb);
-            advance(1);
+            const uint32_t d = acquire(2);
+            tma_load_2d_pair(d, &map_w1, bar(B_RFULL + slot), kb * BK, c * WCOLS + (int)rank * (WCOLS / 2));
+            TL_TRACE(2, 200 + c * 4 + kb);
+            advance(2);
+          }
+        };
+        auto load_f2 = [&](int c, int half) {              // W2 columns of one 128-column half of chunk c: 128 output rows per CTA
+          for (int kb = 0; kb < HCOLS / BK; ++kb) {
+            const uint32_t d = acquire(2);
+            tma_load_2d_pair(d, &map_w2, bar(B_RFULL + slot), c * WCOLS + half * HCOLS + kb * BK, (int)rank * (DM / 2));
+            TL_TRACE(2, 300 + (c * 2 + half) * 2 + kb);
+            advance(2);
           }
         };
         load_f1(0);
-        load_f1(1);
-        for (int i = 0; i < p.n_chunks; ++i) {
-          for (int kb = 0; kb < HCOLS / BK; ++kb) {        // W2 columns of hidden chunk i: 128 output rows per CTA
-            const uint32_t d = acquire(2);
-            tma_load_2d_pair(d, &map_w2, bar(B_RFULL + slot), i * HCOLS + kb * BK, (int)rank * (DM / 2));
-            TL_TRACE(2, 300 + i * 2 + kb);
-            advance(2);
-          }
-          if (i + 2 < p.n_chunks) load_f1(i + 2);
+        for (int c = 0; c < p.n_chunks; ++c) {
+          if (c > 0) load_f2(c - 1, 1);
+          load_f2(c, 0);
+          if (c + 1 < p.n_chunks) load_f1(c + 1);
         }
+        load_f2(p.n_chunks - 1, 1);
       }
     }
   } else if (warp == 1) {
@@ -216,41 +221,51 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
         mbar_wait(bar(B_X1), (uint32_t)(it & 1));
         tc_fence_after();
         TL_TRACE(0, 2);
-        auto ffn1 = [&](int j) {                           // ACC_H[j & 1] = x1 @ W1[chunk j]^T   (N = 128)
-          const uint32_t d = acc_h + (uint32_t)((j & 1) * HCOLS);
+        auto ffn1 = [&](int c) {                           // ACC_H (256 columns) = x1 @ W1[wide chunk c]^T
           for (int kb = 0; kb < DM / BK; ++kb) {
             const uint32_t sb = wait_full();
-            const int sl = next(1);
+            const int sl = next(2);
             const uint64_t adesc = make_smem_desc(xa + (uint32_t)(kb * SUB)), bdesc = make_smem_desc(sb);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k)
-              umma_f16_pair(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N128, (kb | k) != 0 ? 1u : 0u);
-            release(sl, 1);
+              umma_f16_pair(acc_h, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, (kb | k) != 0 ? 1u : 0u);
+            release(sl, 2);
           }
-          umma_commit_pair(bar(B_HFULL + (j & 1)));
-          TL_TRACE(0, 200 + j);
+          umma_commit_pair(bar(B_HFULL));
+          TL_TRACE(0, 200 + c);
         };
-        ffn1(0);
-        ffn1(1);
-        for (int i = 0; i < p.n_chunks; ++i) {
-          const int b = i & 1;
-          // relu(h_i) is in HB[b] (and ACC_H[b] has been read): FFN2 accumulates on top of the parked x1
-          mbar_wait(bar(B_HREADY + b), (uint32_t)((it * HC + (i >> 1)) & 1));
-          tc_fence_after();
-          TL_TRACE(0, 300 + i);
+        auto ffn2 = [&](int c, int half) {                 // ACC_O += relu(h)[half of chunk c] @ W2[:, those 128 columns]^T (on top of x1)
           for (int kb = 0; kb < HCOLS / BK; ++kb) {
             const uint32_t sb = wait_full();
             const int sl = next(2);
-            const uint64_t adesc = make_smem_desc(hb + (uint32_t)((b * 2 + kb) * SUB)), bdesc = make_smem_desc(sb);
+            const uint64_t adesc = make_smem_desc(hb + (uint32_t)((half * 2 + kb) * SUB)), bdesc = make_smem_desc(sb);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k)
               umma_f16_pair(acc_o, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC_N256, 1u);
             release(sl, 2);
           }
-          umma_commit_pair(bar(B_HBFREE + b));
-          TL_TRACE(0, 400 + i);
-          if (i + 2 < p.n_chunks) ffn1(i + 2);
+          umma_commit_pair(bar(B_HBFREE + half));
+          TL_TRACE(0, 400 + c * 2 + half);
+        };
+        // Wide chunks (256 hidden columns, N = 256 MMAs: the x1 operand is read from shared memory once per 256 output columns, not
+        // once per 128) with ONE FFN1 accumulator, handed over in two 128-column halves. Issue order
+        //   F1(c) | F2(c-1, h1) | F2(c, h0) | F1(c+1) | F2(c, h1) | ...
+        // so that the tensor pipe has F2(c-1, h1) to run while the epilogue turns the first half of chunk c around, and F2(c, h0)
+        // while it turns the second.
+        ffn1(0);
+        for (int c = 0; c < p.n_chunks; ++c) {
+          const uint32_t par = (uint32_t)((it * p.n_chunks + c) & 1);
+          if (c > 0) ffn2(c - 1, 1);
+          mbar_wait(bar(B_HREADY + 0), par);               // relu(h) first half of chunk c is in HB[0]
+          tc_fence_after();
+          TL_TRACE(0, 300 + c * 2);
+          ffn2(c, 0);
+          mbar_wait(bar(B_HREADY + 1), par);               // second half in HB[1]; ACC_H has been read completely
+          tc_fence_after();
+          TL_TRACE(0, 301 + c * 2);
+          if (c + 1 < p.n_chunks) ffn1(c + 1);
         }
+        ffn2(p.n_chunks - 1, 1);
         umma_commit_pair(bar(B_O2FULL));
         TL_TRACE(0, 9);
       }
@@ -364,40 +379,42 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
         }
       }
-      for (int i = 0; i < p.n_chunks; ++i) {
-        const int b = i & 1;
-        const int64_t seq = it * HC + (i >> 1);              // completions of this buffer's barriers before this chunk
-        mbar_wait(bar(B_HFULL + b), (uint32_t)(seq & 1));
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const int64_t seq = it * p.n_chunks + c;             // completions of the chunk barriers before this chunk
+        mbar_wait(bar(B_HFULL), (uint32_t)(seq & 1));
         tc_fence_after();
-        TL_TRACE(1, 200 + i);
-        uint32_t r0[CW], r1[CW];
-        tmem_ld16_issue(t_h + (uint32_t)(b * HCOLS), r0);
-        tmem_ld16_issue(t_h + (uint32_t)(b * HCOLS + CW), r1);
-        tmem_ld16_wait(r0);
-        tmem_ld16_wait(r1);
-        const float* b1 = s_par + 6 * DM + i * HCOLS + part * 32;
-        uint4 o[4];
+        TL_TRACE(1, 200 + c);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t* src = c < 2 ? r0 : r1;
-          const int off = (c & 1) * 8;
-          const float4 ba = *reinterpret_cast<const float4*>(b1 + c * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(b1 + c * 8 + 4);
-          __half2* hh = reinterpret_cast<__half2*>(&o[c]);
-          hh[0] = __floats2half2_rn(fmaxf(__uint_as_float(src[off]) + ba.x, 0.f), fmaxf(__uint_as_float(src[off + 1]) + ba.y, 0.f));
-          hh[1] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(src[off + 3]) + ba.w, 0.f));
-          hh[2] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(src[off + 5]) + bb.y, 0.f));
-          hh[3] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(src[off + 7]) + bb.w, 0.f));
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r0[CW], r1[CW];
+          tmem_ld16_issue(t_h + (uint32_t)(half * HCOLS), r0);
+          tmem_ld16_issue(t_h + (uint32_t)(half * HCOLS + CW), r1);
+          tmem_ld16_wait(r0);
+          tmem_ld16_wait(r1);
+          const float* b1 = s_par + 6 * DM + c * WCOLS + half * HCOLS + part * 32;
+          uint4 o[4];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t* src = cc < 2 ? r0 : r1;
+            const int off = (cc & 1) * 8;
+            const float4 ba = *reinterpret_cast<const float4*>(b1 + cc * 8);
+            const float4 bb = *reinterpret_cast<const float4*>(b1 + cc * 8 + 4);
+            __half2* hh = reinterpret_cast<__half2*>(&o[cc]);
+            hh[0] = __floats2half2_rn(fmaxf(__uint_as_float(src[off]) + ba.x, 0.f), fmaxf(__uint_as_float(src[off + 1]) + ba.y, 0.f));
+            hh[1] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(src[off + 3]) + ba.w, 0.f));
+            hh[2] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 4]) + bb.x, 0.f), fmaxf(__uint_as_float(src[off + 5]) + bb.y, 0.f));
+            hh[3] = __floats2half2_rn(fmaxf(__uint_as_float(src[off + 6]) + bb.z, 0.f), fmaxf(__uint_as_float(src[off + 7]) + bb.w, 0.f));
+          }
+          if (seq > 0) mbar_wait(bar(B_HBFREE + half), (uint32_t)((seq - 1) & 1));   // FFN2 of the previous chunk's half has finished reading HB[half]
+          const uint32_t hrow = hb + (uint32_t)((half * 2 + (part >> 1)) * SUB) + (uint32_t)(row * 128);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) sts128(hrow + (uint32_t)(((((part & 1) * 4 + cc) ^ (row & 7)) & 7) << 4), o[cc]);
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(bar(B_HREADY + half));
+          TL_TRACE(1, 300 + c * 2 + half);
         }
-        if (seq > 0) mbar_wait(bar(B_HBFREE + b), (uint32_t)((seq - 1) & 1));     // FFN2 of chunk i-2 has finished reading HB[b]
-        const uint32_t hrow = hb + (uint32_t)((b * 2 + (part >> 1)) * SUB) + (uint32_t)(row * 128);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sts128(hrow + (uint32_t)(((((part & 1) * 4 + c) ^ (row & 7)) & 7) << 4), o[c]);
-        fence_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(bar(B_HREADY + b));
-        TL_TRACE(1, 300 + i);
       }
       // ---------------- LayerNorm2: x = LN(acc + b2) (acc already holds x1 + FFN) -> fp32 stream + fp16 copy
       {
@@ -533,12 +550,12 @@ cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   };
   CUresult r = wmap(&m_wo, t.Wo16, DM, DM, DM / 2);
-  if (r == CUDA_SUCCESS) r = wmap(&m_w1, t.W1_16, DM, t.ffn_dim, HCOLS / 2);
+  if (r == CUDA_SUCCESS) r = wmap(&m_w1, t.W1_16, DM, t.ffn_dim, WCOLS / 2);
   if (r == CUDA_SUCCESS) r = wmap(&m_w2, t.W2_16, t.ffn_dim, DM, DM / 2);
   if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
 
   TlParams p{};
-  p.M = t.M; p.m_tiles = (t.M + BM - 1) / BM; p.n_chunks = t.ffn_dim / HCOLS;
+  p.M = t.M; p.m_tiles = (t.M + BM - 1) / BM; p.n_chunks = t.ffn_dim / WCOLS;
   p.x_in = t.x32; p.x_out = t.x32; p.x16_out = t.x16;
   p.bo = t.bo; p.b1 = t.b1; p.b2 = t.b2; p.ln1_g = t.ln1_g; p.ln1_b = t.ln1_b; p.ln2_g = t.ln2_g; p.ln2_b = t.ln2_b;
   const int64_t total = (p.m_tiles + 1) / 2;
