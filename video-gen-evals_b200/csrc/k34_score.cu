@@ -20,11 +20,11 @@ constexpr int kD = TAG_D_MODEL;
 // Deterministic segmented reduction (utils.py:1035-1041: sums.index_add_(y, z); counts.index_add_(y, 1)).
 // Pass 1: every CTA owns a contiguous block of rows and every warp a contiguous slice of it. A warp fetches the labels of
 // 32 rows with one coalesced load and walks the rows with the label broadcast by warp shuffle; rows of one label run
-// (a video's windows are adjacent) are summed in registers (8 columns per lane, eight rows in flight) and a finished run is
+// (a video's windows are adjacent) are summed in registers (8 columns per lane, four rows being summed while the next four are in flight) and a finished run is
 // added to the warp's PRIVATE [C][257] accumulator in shared memory (plain read-modify-write: no atomics anywhere). The
 // warps' accumulators are combined in warp order into one partial per CTA. Pass 2 adds the CTA partials in CTA order into
 // sums_counts. The order of every floating-point addition is a function of (n, C) only: results are bit-identical run to run.
-constexpr int kRows = 8;   // rows (1 KB each) a warp keeps in flight
+constexpr int kRows = 4;   // rows (1 KB each) per batch; two batches in flight
 __device__ __forceinline__ int k3_slot(int col) { return (col & 7) * 32 + (col >> 3); }   // lane-major layout: conflict-free flushes
 
 __global__ void __launch_bounds__(256) k_centroid_partial(const float* __restrict__ z, const int32_t* __restrict__ labels,
@@ -58,15 +58,24 @@ __global__ void __launch_bounds__(256) k_centroid_partial(const float* __restric
   for (int64_t base = r0; base < r1; base += 32) {
     const int m = (int)min((int64_t)32, r1 - base);
     const int my_label = lane < m ? __ldg(labels + base + lane) : -1;
+    // four rows are summed while the next four are already in flight (4-8 KB per warp outstanding at any time)
+    float nxt[kRows][8];
+#pragma unroll
+    for (int j = 0; j < kRows; ++j)
+      if (j < m) Row8<float>::load(z + (base + j) * kD + lane * 8, nxt[j]);
     for (int i0 = 0; i0 < m; i0 += kRows) {
       float v[kRows][8];
       int y[kRows];
 #pragma unroll
       for (int j = 0; j < kRows; ++j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[j][k] = nxt[j][k];
         y[j] = __shfl_sync(FULL_MASK, my_label, (i0 + j) & 31);
         if (i0 + j >= m) y[j] = -1;
-        if (y[j] >= 0 && y[j] < C) Row8<float>::load(z + (base + i0 + j) * kD + lane * 8, v[j]);
       }
+#pragma unroll
+      for (int j = 0; j < kRows; ++j)
+        if (i0 + kRows + j < m) Row8<float>::load(z + (base + i0 + kRows + j) * kD + lane * 8, nxt[j]);
 #pragma unroll
       for (int j = 0; j < kRows; ++j) {
         if (i0 + j >= m) break;
