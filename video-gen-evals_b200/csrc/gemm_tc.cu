@@ -755,6 +755,7 @@ struct TcContext {
   int num_sms = 148;
   bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
   int dbg = 0;            // TAG_TC_DEBUG bottleneck experiments (results are wrong when set)
+  int b_stage_cap = 0;    // experiments build: TAG_TC_BSTAGES caps the weight stages of halo mode (latency-sensitivity probe)
   int halo_a_stages = 2;  // activation chunks in flight in halo mode (2..4; 3 and 4 measured no faster, and slower at dilation 8
                           // where they leave only 4 weight stages — profiles/r2_halo_microbench.log)
   int halo = 2;           // conv activation loads: 2 (default) = halo tiles for every dilation — one load per 64-channel chunk, the five
@@ -793,6 +794,8 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   if (env != nullptr) c->dbg = atoi(env);
   env = getenv("TAG_TC_HALO");
   if (env != nullptr) c->halo = atoi(env);
+  env = getenv("TAG_TC_BSTAGES");
+  if (env != nullptr) c->b_stage_cap = atoi(env);
   env = getenv("TAG_TC_HALO_ASTAGES");
   if (env != nullptr) { c->halo_a_stages = atoi(env); if (c->halo_a_stages < 2) c->halo_a_stages = 2; if (c->halo_a_stages > MAX_A_STAGES) c->halo_a_stages = MAX_A_STAGES; }
 #endif
@@ -886,6 +889,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
         p.halo = (!aligned && ctx->halo == 3) ? 2 : 1;
         p.a_stage_bytes = a_stage; p.a_box_bytes = rows * 128; p.a_stages = a_stages;
         p.b_stages = b_stages < MAX_STAGES ? b_stages : MAX_STAGES;
+        if (ctx->b_stage_cap > 0 && p.b_stages > ctx->b_stage_cap) p.b_stages = ctx->b_stage_cap;
         p.tap_rows = g.dil * nw;
         p.lw = nw > 1 ? lw : 0; p.lt = lt;
       }
