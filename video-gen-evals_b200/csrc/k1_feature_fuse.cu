@@ -391,8 +391,14 @@ __global__ void __launch_bounds__(256) k_feature_fuse_staged(const FuseParams p,
     uint32_t ok = 0;
     const long long c0 = clock64();
     while (!ok) {
+#ifndef TAG_MBAR_NO_HINT
+      // suspend-time hint: the warp is parked until the copies land instead of polling (see tc_common.cuh)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(0), "r"(200000u) : "memory");
+#else
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok) : "r"(bar), "r"(0) : "memory");
+#endif
       if (!ok && clock64() - c0 > 4000000000LL) __trap();
     }
   }

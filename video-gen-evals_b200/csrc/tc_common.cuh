@@ -31,16 +31,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
+// The try_wait carries a suspend-time hint: the hardware parks the thread until the phase completes (or the hint expires) instead
+// of returning after its short default time-out. Without it the 16 epilogue warps of a GEMM CTA, which wait for an accumulator
+// 20-45 % of the time, spent that time executing this loop — ncu: half of the conv1 kernel's warp instructions were
+// try_wait / branch / clock / compare — taking issue slots and power from the warps that had work.
+#ifndef TAG_MBAR_NO_HINT
+#define TAG_MBAR_HINT_OPERAND ", %3"
+#else
+#define TAG_MBAR_HINT_OPERAND
+#endif
+constexpr uint32_t kMbarSuspendNs = 200000u;
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   const long long t0 = clock64();
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2" TAG_MBAR_HINT_OPERAND ";\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
     if (ok) break;
     if (clock64() - t0 > 4000000000LL) {
@@ -113,10 +124,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2" TAG_MBAR_HINT_OPERAND ";\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
     if (ok) break;
     if (clock64() - t0 > 4000000000LL) {
