@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B: mbarrier waits with the suspend-time hint (product library) vs without (experiments build made with TAG_BUILD_NO_HINT=1)
+# A/B: mbarrier waits with the suspend-time product library vs the experiments build made with an A/B compile flag (TAG_BUILD_NO_HINT=1, TAG_BUILD_ALL_POLL=1)
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_tc.py tests/test_gpu_kernels.py -m gpu -q -x -k "gemm_tc or tlayer or encoder or feature_fuse or fused_pipeline" 2>&1 | tail -3
 for which in exp prod exp prod; do

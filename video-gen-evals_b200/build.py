@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False, experiments: bool = False)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "tag_b200.h"))
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DTAG_EXPERIMENTS"] + (["-DTAG_MBAR_NO_HINT"] if os.environ.get("TAG_BUILD_NO_HINT") else []) if experiments else [])
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-DTAG_EXPERIMENTS"] + (["-DTAG_MBAR_NO_HINT"] if os.environ.get("TAG_BUILD_NO_HINT") else []) + (["-DTAG_EPI_LEADER_POLL"] if os.environ.get("TAG_BUILD_LEADER_POLL") else []) if experiments else [])
 
     def compile_one(src):
         sp = os.path.join(CSRC, src)

@@ -175,6 +175,22 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
 // (post-norm, reference model.py:145): y = LN(acc + bias + x) * gamma + beta, x the fp32 token stream. The pre-norm sum
 // is parked in the accumulator's own TMEM columns (tcgen05.st) between the statistics pass and the normalise pass, so
 // neither registers nor shared memory have to hold the 128 x 256 fp32 tile.
+// Every epilogue warp waits on the accumulator-full mbarrier itself (parked by the suspend-time hint, tc_common.cuh). The
+// alternative — ONE warp watches the mbarrier and the other 15 park at a hardware named barrier, where a waiting warp issues
+// nothing — was measured (TAG_EPI_LEADER_POLL, experiments build; same-box A/B in profiles/r2_mbar_hint_ab.log): conv GEMMs
+// +1 %, but the epilogue-bound small-K GEMMs -2 % (the per-tile rendezvous couples the 16 warps), nothing on the step.
+constexpr int kEpiStartBarrier = 9;
+__device__ __forceinline__ void epi_wait_accumulator(uint32_t bar, uint32_t parity, int warp) {
+#ifdef TAG_EPI_LEADER_POLL
+  if (warp == 2) mbar_wait(bar, parity);
+  asm volatile("bar.sync %0, %1;" ::"r"(kEpiStartBarrier), "r"(EPI_WARPS * 32) : "memory");
+#else
+  (void)warp;
+  mbar_wait(bar, parity);
+#endif
+  tc_fence_after();
+}
+
 template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
@@ -408,8 +424,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         float s1 = 0.f, s2 = 0.f;
         uint4 rres[4];
         unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
+        epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {                           // units of 32 fp16 columns
           unit_to_smem(stg, lane, rres);
@@ -531,8 +546,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         float s1 = 0.f, s2 = 0.f;
         uint4 rres[4];
         unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, rm, p.M, (int64_t)n_base * 4, lane, rres);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
+        epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           unit_to_smem(stg, lane, rres);
@@ -618,8 +632,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const int ya = j0 < p.tcl_valid ? __ldg(p.tcl_y + j0) : kPadLabel;
         const int yb = j1 < p.tcl_valid ? __ldg(p.tcl_y + j1) : kPadLabel;
         float e_pos = 0.f, en_pos = 0.f, e_neg = 0.f, s_pos = 0.f, n_pos = 0.f;
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
+        epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           uint32_t raw[CW];
@@ -654,8 +667,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const bool row_is_t0 = p.row0_vec != nullptr && ((tile_row(rm.tile_base, rm.rt0 + lane, rm.lw, rm.lt) & (int64_t)(p.T - 1)) == 0);
         uint4 rres[4];
         if (has_res) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
+        epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (has_res) {
@@ -702,8 +714,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const bool has_res = p.res32 != nullptr;
         uint4 rres[4];
         if (has_res) unit_load(reinterpret_cast<const char*>(p.res32), (int64_t)p.N * 4, rm, p.M, (int64_t)n_base * 4, lane, rres);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
+        epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           if (has_res) {
