@@ -108,6 +108,8 @@ struct TcParams {
   float* tcl_part;         // [M][N / 64][5]: sum_pos exp(S/t), sum_pos exp(-S), sum_neg exp(S/t), sum_pos S/t, #pos
   float tcl_inv_temp;
   int tcl_valid;           // columns >= tcl_valid are padding (N rounded up to 256)
+  int c_tma;               // fp16 output through TMA stores of the staging tiles: 0 off, 1 rows linear (2-D map), 2 (t, window)-ordered
+                           //   halo tiles (3-D map: column, window, frame)
   int dbg;                 // bottleneck experiments (TAG_TC_DEBUG): 1 no epilogue stores, 2 no weight loads, 4 no activation loads
   // halo mode (conv): A chunk loaded once per 64 channels with its time halo, taps = shifted descriptor views
   int halo;                // 0 off, 1 on, 2 on with the descriptor base-offset field set for unaligned tap shifts (experiment)
@@ -175,6 +177,42 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
 // (post-norm, reference model.py:145): y = LN(acc + bias + x) * gamma + beta, x the fp32 token stream. The pre-norm sum
 // is parked in the accumulator's own TMEM columns (tcgen05.st) between the statistics pass and the normalise pass, so
 // neither registers nor shared memory have to hold the 128 x 256 fp32 tile.
+// ---- fp16 output through TMA stores (round 2). The per-warp staging tile (32 rows x 64 B, 16-byte chunks XOR-ed with
+// (row >> 1) & 3) IS the SWIZZLE_64B layout of a [32 rows x 32 fp16] TMA box, so one elected lane can hand the whole tile to the
+// TMA engine instead of every lane re-reading it (LDS) and issuing predicated 16-byte global stores with 64-bit row arithmetic:
+// fewer instructions on a power-capped board, no LSU work, and the M edge is clipped by the tensor map. For halo tiles the
+// 32 rows of a warp are (frame, window)-ordered, which is a 3-D box (32 columns, NW windows, 32 / NW frames).
+__device__ __forceinline__ void stg_reuse_wait(int lane) {     // the previous store of this warp has finished READING the staging tile
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+__device__ __forceinline__ void stg_store_drain(int lane) {    // all stores of this warp have completed (before the CTA exits)
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+__device__ __forceinline__ void tma_store_unit(const CUtensorMap* map, const TcParams& p, uint32_t stg, int64_t m_tile, int q, int col,
+                                               int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // this lane's st.shared -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    if (p.c_tma == 1) {
+      const int row = (int)(m_tile * BLOCK_M) + q * 32;
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                   ::"l"(reinterpret_cast<uint64_t>(map)), "r"(stg), "r"(col), "r"(row) : "memory");
+    } else {
+      const int nw = 1 << p.lw;
+      int w, t;
+      if (p.mode == 1) { w = (int)(m_tile * p.wpt); t = 0; }
+      else { w = (int)(m_tile / p.tpw); t = (int)(m_tile - (int64_t)w * p.tpw) * BLOCK_M; }
+      if (nw >= 32) w += (q * 32) & (nw - 1);
+      t += (q * 32) >> p.lw;
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(reinterpret_cast<uint64_t>(map)), "r"(stg), "r"(col), "r"(w), "r"(t) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 // Every epilogue warp waits on the accumulator-full mbarrier itself (parked by the suspend-time hint, tc_common.cuh). The
 // alternative — ONE warp watches the mbarrier and the other 15 park at a hardware named barrier, where a waiting warp issues
 // nothing — was measured (TAG_EPI_LEADER_POLL, experiments build; same-box A/B in profiles/r2_mbar_hint_ab.log): conv GEMMs
@@ -193,7 +231,8 @@ __device__ __forceinline__ void epi_wait_accumulator(uint32_t bar, uint32_t pari
 
 template <int MODE, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+          const __grid_constant__ CUtensorMap map_c, const TcParams p) {
   constexpr int STAGES = Cfg<PAIR>::STAGES;
   constexpr int STAGE_BYTES = Cfg<PAIR>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -425,6 +464,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         uint4 rres[4];
         unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
         epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
+        if (p.c_tma) stg_reuse_wait(lane);                      // the previous tile's last TMA store has read the staging tile
 #pragma unroll
         for (int u = 0; u < 2; ++u) {                           // units of 32 fp16 columns
           unit_to_smem(stg, lane, rres);
@@ -535,11 +575,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
               hh[e] = __floats2half2_rn(fmaf(fmaf(z.x, rstd, nmr), gg[2 * e], bb[2 * e]),
                                         fmaf(fmaf(z.y, rstd, nmr), gg[2 * e + 1], bb[2 * e + 1]));
             }
+            if (i == 0 && u == 1 && p.c_tma) stg_reuse_wait(lane);   // unit 0's store has read the tile
             sts128(stg_addr(stg, lane, i), o);
           }
-          __syncwarp();
-          unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(nl + u * 32) * 2, lane, stg);
-          __syncwarp();
+          if (p.c_tma) {
+            tma_store_unit(&map_c, p, stg, m_tile, q, n_tile * BLOCK_N + nl + u * 32, lane);
+          } else {
+            __syncwarp();
+            unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(nl + u * 32) * 2, lane, stg);
+            __syncwarp();
+          }
         }
       } else if constexpr (LN) {
         // ---- pass 1: v = acc + bias + x (fp32 residual, staged coalesced), row sums, v parked back into TMEM
@@ -671,6 +716,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (has_res) {
+            if (p.c_tma) stg_reuse_wait(lane);
             unit_to_smem(stg, lane, rres);
             __syncwarp();
             if (u == 0) unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)(n_base + 32) * 2, lane, rres);
@@ -691,6 +737,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
                 v[i] = z.x; v[i + 1] = z.y; v[i + 2] = z.z; v[i + 3] = z.w;
               }
             }
+            if (cc == 0 && !has_res && p.c_tma) stg_reuse_wait(lane);   // the previous unit's TMA store has read the staging tile
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               uint4 o;
@@ -705,9 +752,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
           }
-          __syncwarp();
-          if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(n_base + u * 32) * 2, lane, stg);
-          __syncwarp();
+          if (p.c_tma) {
+            if (!(p.dbg & 1)) tma_store_unit(&map_c, p, stg, m_tile, q, n_base + u * 32, lane);
+          } else {
+            __syncwarp();
+            if (!(p.dbg & 1)) unit_store(reinterpret_cast<char*>(p.C16), (int64_t)p.ldc * 2, rm, p.M, (int64_t)(n_base + u * 32) * 2, lane, stg);
+            __syncwarp();
+          }
         }
       } else {
         // ---- fp32 output (optional fp32 residual, ld = N): 4 units of 16 columns
@@ -745,6 +796,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
     }
   }
 
+  if (warp >= 2 && p.c_tma) stg_store_drain(lane);
   tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();     // no CTA exits (or frees TMEM) while its partner may still signal / read it
@@ -766,6 +818,7 @@ struct TcContext {
   int num_sms = 148;
   bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
   int dbg = 0;            // TAG_TC_DEBUG bottleneck experiments (results are wrong when set)
+  bool tma_store = true;  // fp16 outputs leave through TMA stores of the staging tiles (TAG_TC_TMA_STORE=0 in the experiments build: A/B)
   int b_stage_cap = 0;    // experiments build: TAG_TC_BSTAGES caps the weight stages of halo mode (latency-sensitivity probe)
   int halo_a_stages = 2;  // activation chunks in flight in halo mode (2..4; 3 and 4 measured no faster, and slower at dilation 8
                           // where they leave only 4 weight stages — profiles/r2_halo_microbench.log)
@@ -805,6 +858,8 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   if (env != nullptr) c->dbg = atoi(env);
   env = getenv("TAG_TC_HALO");
   if (env != nullptr) c->halo = atoi(env);
+  env = getenv("TAG_TC_TMA_STORE");
+  if (env != nullptr) c->tma_store = env[0] != '0';
   env = getenv("TAG_TC_BSTAGES");
   if (env != nullptr) c->b_stage_cap = atoi(env);
   env = getenv("TAG_TC_HALO_ASTAGES");
@@ -973,6 +1028,29 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(W) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
 
+  CUtensorMap map_c;
+  memset(&map_c, 0, sizeof(map_c));
+  if (ctx->tma_store && g.C16 != nullptr && !ln && !tcl && g.ldc % 8 == 0 && reinterpret_cast<uintptr_t>(g.C16) % 16 == 0) {
+    CUresult rc3;
+    if (p.halo) {
+      const int nw = 1 << p.lw, bw = nw < 32 ? nw : 32;
+      cuuint64_t cdim[3] = {(cuuint64_t)g.N, (cuuint64_t)(g.M / g.T), (cuuint64_t)g.T};
+      cuuint64_t cstr[2] = {(cuuint64_t)g.T * g.ldc * 2, (cuuint64_t)g.ldc * 2};
+      cuuint32_t cbox[3] = {32, (cuuint32_t)bw, (cuuint32_t)(32 / bw)};
+      rc3 = ctx->encode(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, g.C16, cdim, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p.c_tma = 2;
+    } else {
+      cuuint64_t cdim[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+      cuuint64_t cstr[1] = {(cuuint64_t)g.ldc * 2};
+      cuuint32_t cbox[2] = {32, 32};
+      rc3 = ctx->encode(&map_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, g.C16, cdim, cstr, cbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      p.c_tma = 1;
+    }
+    if (rc3 != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(C) failed with CUresult %d", (int)rc3); return cudaErrorInvalidValue; }
+  }
+
   if (pair) {
     const int64_t total = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int64_t clusters = total < ctx->num_sms / 2 ? total : ctx->num_sms / 2;
@@ -985,16 +1063,16 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (tcl) return cudaLaunchKernelEx(&cfg, k_gemm_tc<3, true>, map_a, map_b, p);
-    if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<1, true>, map_a, map_b, p);
-    if (ln) return cudaLaunchKernelEx(&cfg, k_gemm_tc<2, true>, map_a, map_b, p);
-    return cudaLaunchKernelEx(&cfg, k_gemm_tc<0, true>, map_a, map_b, p);
+    if (tcl) return cudaLaunchKernelEx(&cfg, k_gemm_tc<3, true>, map_a, map_b, map_c, p);
+    if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<1, true>, map_a, map_b, map_c, p);
+    if (ln) return cudaLaunchKernelEx(&cfg, k_gemm_tc<2, true>, map_a, map_b, map_c, p);
+    return cudaLaunchKernelEx(&cfg, k_gemm_tc<0, true>, map_a, map_b, map_c, p);
   }
   const int64_t total = p.m_tiles * p.n_tiles;
   const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
-  if (tcl) k_gemm_tc<3, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
-  else if (gn) k_gemm_tc<1, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
-  else if (ln) k_gemm_tc<2, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
-  else k_gemm_tc<0, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, p);
+  if (tcl) k_gemm_tc<3, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+  else if (gn) k_gemm_tc<1, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+  else if (ln) k_gemm_tc<2, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+  else k_gemm_tc<0, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
   return cudaGetLastError();
 }
