@@ -125,17 +125,20 @@ struct TcParams {
 
 // v = act(acc + bias + res) for CW consecutive columns of one row; the residual comes from the staging tile
 // (RES = 0 none, 16: two 16-byte chunks of fp16, 32: four 16-byte chunks of fp32)
-template <int RES>
+template <int RES, int ACT>
 __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&raw)[CW], uint32_t stg, int lane, int chunk0,
                                            float (&v)[CW], int n) {
+  // per-element arithmetic on packed fp32 pairs (FFMA2 / FADD2: one issue slot per two elements)
+  f32x2 w[CW / 2];
 #pragma unroll
-  for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(raw[i]);
-  if (p.bias != nullptr) {
+  for (int i = 0; i < CW / 2; ++i) w[i] = pk2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
+  // no branch between the TMEM load and the stores: register pairs that live across a branch cost a copy per register
+  // (the host passes a zero vector when the GEMM has no bias; the activation is a template parameter of the kernel)
 #pragma unroll
-    for (int i = 0; i < CW; i += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-      v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-    }
+  for (int i = 0; i < CW; i += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+    w[i / 2] = add2(w[i / 2], pk2(b.x, b.y));
+    w[i / 2 + 1] = add2(w[i / 2 + 1], pk2(b.z, b.w));
   }
   if constexpr (RES == 16) {
 #pragma unroll
@@ -143,21 +146,24 @@ __device__ __forceinline__ void epi_values(const TcParams& p, const uint32_t (&r
       const uint4 u = lds128(stg_addr(stg, lane, chunk0 + i));
       const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); v[i * 8 + 2 * e] += f.x; v[i * 8 + 2 * e + 1] += f.y; }
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(hh[e]); w[i * 4 + e] = add2(w[i * 4 + e], pk2(f.x, f.y)); }
     }
   }
   if constexpr (RES == 32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint4 u = lds128(stg_addr(stg, lane, i));
-      v[i * 4] += __uint_as_float(u.x); v[i * 4 + 1] += __uint_as_float(u.y);
-      v[i * 4 + 2] += __uint_as_float(u.z); v[i * 4 + 3] += __uint_as_float(u.w);
+      w[i * 2] = add2(w[i * 2], pk2(__uint_as_float(u.x), __uint_as_float(u.y)));
+      w[i * 2 + 1] = add2(w[i * 2 + 1], pk2(__uint_as_float(u.z), __uint_as_float(u.w)));
     }
   }
-  if (p.act == 1) {
+  if constexpr (ACT == 1) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = gelu_fast(v[i]);
-  } else if (p.act == 2) {
+    for (int i = 0; i < CW / 2; ++i) w[i] = gelu_fast2(w[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < CW / 2; ++i) upk2(w[i], v[2 * i], v[2 * i + 1]);
+  if constexpr (ACT == 2) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
   }
@@ -229,7 +235,7 @@ __device__ __forceinline__ void epi_wait_accumulator(uint32_t bar, uint32_t pari
   tc_fence_after();
 }
 
-template <int MODE, bool PAIR>
+template <int MODE, bool PAIR, int ACT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
           const __grid_constant__ CUtensorMap map_c, const TcParams p) {
@@ -460,7 +466,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       if constexpr (GN) {
         // ---- pass 1: z = GELU(acc + res), per-row partial sums, z stashed as fp16 pairs in registers
         uint32_t stash[EPI_COLS / 2];
-        float s1 = 0.f, s2 = 0.f;
+        f32x2 s1p = pk2(0.f), s2p = pk2(0.f);                   // even / odd columns
         uint4 rres[4];
         unit_load(reinterpret_cast<const char*>(p.res16), (int64_t)p.ldr * 2, rm, p.M, (int64_t)n_base * 2, lane, rres);
         epi_wait_accumulator(tfull_bar(acc), acc_phase, warp);
@@ -477,13 +483,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
             tmem_ld16_wait(raw);
             float v[CW];
-            epi_values<16>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+            epi_values<16, 1>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
             if (!my_row_valid) {
 #pragma unroll
               for (int i = 0; i < CW; ++i) v[i] = 0.f;
             }
 #pragma unroll
-            for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+            for (int i = 0; i < CW / 2; ++i) {
+              const f32x2 vv = pk2(v[2 * i], v[2 * i + 1]);
+              s1p = add2(s1p, vv);
+              s2p = fma2(vv, vv, s2p);
+            }
 #pragma unroll
             for (int i = 0; i < CW / 2; ++i) {
               const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
@@ -496,6 +506,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+        float s1, s2;
+        { float a, b; upk2(s1p, a, b); s1 = a + b; upk2(s2p, a, b); s2 = a + b; }
         // ---- window statistics: rows of a window = min(T,32) lanes x max(1,T/32) quarters x 4 column parts
         const uint32_t red = bar_base + (uint32_t)BAR_BYTES + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
         float S1 = 0.f, S2 = 0.f;
@@ -554,6 +566,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
         const float var = fmaxf(S2 * inv_n - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
+        const f32x2 rstd2 = pk2(rstd), nmr2 = pk2(nmr);
         // ---- pass 2: normalise the stash, per-channel affine (from shared memory), stage, store coalesced
         const int nl = part * EPI_COLS;
 #pragma unroll
@@ -572,8 +585,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 z = __half22float2(*reinterpret_cast<const __half2*>(&stash[u * 16 + i * 4 + e]));
-              hh[e] = __floats2half2_rn(fmaf(fmaf(z.x, rstd, nmr), gg[2 * e], bb[2 * e]),
-                                        fmaf(fmaf(z.y, rstd, nmr), gg[2 * e + 1], bb[2 * e + 1]));
+              const f32x2 o2 = fma2(fma2(pk2(z.x, z.y), rstd2, nmr2), pk2(gg[2 * e], gg[2 * e + 1]), pk2(bb[2 * e], bb[2 * e + 1]));
+              float oa, ob;
+              upk2(o2, oa, ob);
+              hh[e] = __floats2half2_rn(oa, ob);
             }
             if (i == 0 && u == 1 && p.c_tma) stg_reuse_wait(lane);   // unit 0's store has read the tile
             sts128(stg_addr(stg, lane, i), o);
@@ -601,7 +616,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
           tmem_ld16_wait(raw);
           float v[CW];
-          epi_values<32>(p, raw, stg, lane, 0, v, n_base + u * CW);
+          epi_values<32, 0>(p, raw, stg, lane, 0, v, n_base + u * CW);
 #pragma unroll
           for (int i = 0; i < CW; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); raw[i] = __float_as_uint(v[i]); }
           tmem_st16(t_row + (uint32_t)(u * CW), raw);
@@ -728,8 +743,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
             tmem_ld16_wait(raw);
             float v[CW];
-            if (has_res) epi_values<16>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
-            else epi_values<0>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+            if (has_res) epi_values<16, ACT>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
+            else epi_values<0, ACT>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
             if (row_is_t0) {                                   // first frame of a window: the fixed zero-motion row
 #pragma unroll
               for (int i = 0; i < CW; i += 4) {
@@ -777,8 +792,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
           tmem_ld16_issue(t_row + (uint32_t)(u * CW), raw);
           tmem_ld16_wait(raw);
           float v[CW];
-          if (has_res) epi_values<32>(p, raw, stg, lane, 0, v, n_base + u * CW);
-          else epi_values<0>(p, raw, stg, lane, 0, v, n_base + u * CW);
+          if (has_res) epi_values<32, ACT>(p, raw, stg, lane, 0, v, n_base + u * CW);
+          else epi_values<0, ACT>(p, raw, stg, lane, 0, v, n_base + u * CW);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             sts128(stg_addr(stg, lane, i), make_uint4(__float_as_uint(v[i * 4]), __float_as_uint(v[i * 4 + 1]),
@@ -813,7 +828,24 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 
+// the epilogue activation is a template parameter of the plain kernel (MODE 0); GroupNorm always follows a GELU
+typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+GemmKernel pick_kernel(bool pair, int mode, int act) {
+  if (pair) {
+    if (mode == 3) return k_gemm_tc<3, true, 0>;
+    if (mode == 2) return k_gemm_tc<2, true, 0>;
+    if (mode == 1) return k_gemm_tc<1, true, 1>;
+    return act == 1 ? k_gemm_tc<0, true, 1> : act == 2 ? k_gemm_tc<0, true, 2> : k_gemm_tc<0, true, 0>;
+  }
+  if (mode == 3) return k_gemm_tc<3, false, 0>;
+  if (mode == 2) return k_gemm_tc<2, false, 0>;
+  if (mode == 1) return k_gemm_tc<1, false, 1>;
+  return act == 1 ? k_gemm_tc<0, false, 1> : act == 2 ? k_gemm_tc<0, false, 2> : k_gemm_tc<0, false, 0>;
+}
+constexpr int kZeroBiasFloats = 16384;
+
 struct TcContext {
+  float* zero_bias = nullptr;   // bias of a GEMM that has none (the epilogue adds its bias unconditionally)
   EncodeTiledFn encode = nullptr;
   int num_sms = 148;
   bool pair = true;       // CTA pairs (cta_group::2); TAG_TC_PAIR=0 selects the 1-CTA kernel (A/B testing)
@@ -843,14 +875,16 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   c->encode = reinterpret_cast<EncodeTiledFn>(fn);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-  e = cudaFuncSetAttribute(k_gemm_tc<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tc<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaSuccess;
+  for (int pair = 0; pair < 2 && e == cudaSuccess; ++pair)
+    for (int mode = 0; mode < 4 && e == cudaSuccess; ++mode)
+      for (int act = 0; act < (mode == 0 ? 3 : 1) && e == cudaSuccess; ++act)
+        e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pick_kernel(pair != 0, mode, mode == 1 ? 1 : act)),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) {
+    e = cudaMalloc(reinterpret_cast<void**>(&c->zero_bias), (size_t)kZeroBiasFloats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(c->zero_bias, 0, (size_t)kZeroBiasFloats * sizeof(float));
+  }
 #ifdef TAG_EXPERIMENTS   // tools/ build only (build.py --experiments -> libtag_b200_exp.so): the product library reads no environment
   const char* env = getenv("TAG_TC_PAIR");
   if (env != nullptr) c->pair = env[0] != '0';
@@ -873,7 +907,10 @@ TcContext* tc_context_create(int device, char* err, int errlen) {
   return c;
 }
 
-void tc_context_destroy(TcContext* c) { delete c; }
+void tc_context_destroy(TcContext* c) {
+  if (c != nullptr && c->zero_bias != nullptr) cudaFree(c->zero_bias);
+  delete c;
+}
 void* tc_encode_fn(const TcContext* c) { return c ? reinterpret_cast<void*>(c->encode) : nullptr; }
 int tc_num_sms(const TcContext* c) { return c ? c->num_sms : 148; }
 bool tc_pair_enabled(const TcContext* c) { return c != nullptr && c->pair; }
@@ -916,7 +953,9 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
 
   TcParams p{};
   p.M = g.M; p.N = g.N; p.kb_per_tap = g.K / BLOCK_K; p.taps = g.taps; p.dil = g.dil; p.T = g.T;
-  p.bias = g.bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
+  if (g.bias == nullptr && g.N > kZeroBiasFloats) return bad("a GEMM without bias needs N <= 16384");
+  if (g.act < 0 || g.act > 2 || (g.gn_gamma != nullptr && g.act != 1)) return bad("act must be 0 (none), 1 (GELU) or 2 (ReLU); the fused GroupNorm follows a GELU");
+  p.bias = g.bias != nullptr ? g.bias : ctx->zero_bias; p.res16 = g.res16; p.ldr = g.ldr; p.res32 = g.res32; p.C16 = g.C16; p.ldc = g.ldc; p.C32 = g.C32; p.act = g.act;
   p.gn_gamma = g.gn_gamma; p.gn_beta = g.gn_beta;
   p.ln_gamma = g.ln_gamma; p.ln_beta = g.ln_beta;
   p.tcl_y = g.tcl_y; p.tcl_part = g.tcl_part; p.tcl_inv_temp = g.tcl_inv_temp; p.tcl_valid = g.tcl_valid;
@@ -1051,6 +1090,7 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     if (rc3 != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(C) failed with CUresult %d", (int)rc3); return cudaErrorInvalidValue; }
   }
 
+  const int kmode = tcl ? 3 : gn ? 1 : ln ? 2 : 0;
   if (pair) {
     const int64_t total = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int64_t clusters = total < ctx->num_sms / 2 ? total : ctx->num_sms / 2;
@@ -1063,16 +1103,10 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (tcl) return cudaLaunchKernelEx(&cfg, k_gemm_tc<3, true>, map_a, map_b, map_c, p);
-    if (gn) return cudaLaunchKernelEx(&cfg, k_gemm_tc<1, true>, map_a, map_b, map_c, p);
-    if (ln) return cudaLaunchKernelEx(&cfg, k_gemm_tc<2, true>, map_a, map_b, map_c, p);
-    return cudaLaunchKernelEx(&cfg, k_gemm_tc<0, true>, map_a, map_b, map_c, p);
+    return cudaLaunchKernelEx(&cfg, pick_kernel(true, kmode, p.act), map_a, map_b, map_c, p);
   }
   const int64_t total = p.m_tiles * p.n_tiles;
   const int grid = (int)(total < ctx->num_sms ? total : ctx->num_sms);
-  if (tcl) k_gemm_tc<3, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
-  else if (gn) k_gemm_tc<1, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
-  else if (ln) k_gemm_tc<2, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
-  else k_gemm_tc<0, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+  pick_kernel(false, kmode, p.act)<<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
   return cudaGetLastError();
 }
