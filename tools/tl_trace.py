@@ -56,5 +56,7 @@ t0 = ev[0][0]
 # print tiles 2 and 3 of the pair (steady state): find the 3rd occurrence of (mma, 1)
 starts = [i for i, e in enumerate(ev) if e[1] == "mma" and e[2] == 1]
 lo, hi = starts[2], starts[4]
+only = os.environ.get("TL_ROLE")          # e.g. TL_ROLE=epi: one role only
 for clk, who, tag in ev[lo - 12:hi]:
-    print(f"{clk - ev[lo][0]:8d}  {who}  {tag}")
+    if only is None or who == only:
+        print(f"{clk - ev[lo][0]:8d}  {who}  {tag}")

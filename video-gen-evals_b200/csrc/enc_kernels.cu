@@ -285,7 +285,10 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h2(const MergeParams p) {
   const int64_t r = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 5) * 2 + (lane >> 4);
   const bool live = r < p.R;
   const int c0 = sub * 8, c1 = 128 + sub * 8;
-  float d[MM][16], s1[MM];
+  // all per-element arithmetic on packed fp32 pairs (FADD2 / FFMA2): the kernel is bound by instruction issue, and 56 % of its
+  // instructions were scalar FFMA / FADD / FMUL (ncu, profiles/r2_ncu_pass_summary.md)
+  f32x2 d[MM][8];
+  float s1[MM];
 #pragma unroll
   for (int m = 0; m < MM; ++m) {
     uint4 ua = make_uint4(0u, 0u, 0u, 0u), ub = ua;
@@ -296,38 +299,48 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h2(const MergeParams p) {
     }
     const __half2* ha = reinterpret_cast<const __half2*>(&ua);
     const __half2* hb = reinterpret_cast<const __half2*>(&ub);
-    s1[m] = 0.f;
+    f32x2 acc = pk2(0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 a = __half22float2(ha[i]), b = __half22float2(hb[i]);
-      d[m][2 * i] = a.x; d[m][2 * i + 1] = a.y; d[m][8 + 2 * i] = b.x; d[m][8 + 2 * i + 1] = b.y;
-      s1[m] += (a.x + a.y) + (b.x + b.y);
+      d[m][i] = pk2(a.x, a.y); d[m][4 + i] = pk2(b.x, b.y);
+      acc = add2(acc, add2(d[m][i], d[m][4 + i]));
     }
+    float lo, hi;
+    upk2(acc, lo, hi);
+    s1[m] = lo + hi;
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
 #pragma unroll
     for (int m = 0; m < MM; ++m) s1[m] += __shfl_xor_sync(FULL_MASK, s1[m], o);
   }
-  float s2[MM], sq[MM];
+  f32x2 s2p[MM], sqp[MM];
 #pragma unroll
-  for (int m = 0; m < MM; ++m) { s2[m] = 0.f; sq[m] = 0.f; }
+  for (int m = 0; m < MM; ++m) { s2p[m] = pk2(0.f); sqp[m] = pk2(0.f); }
 #pragma unroll
   for (int hblk = 0; hblk < 2; ++hblk) {
     const float4 q0 = *reinterpret_cast<const float4*>(s_gq + (hblk ? c1 : c0));
     const float4 q1 = *reinterpret_cast<const float4*>(s_gq + (hblk ? c1 : c0) + 4);
-    const float gq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const f32x2 gq[4] = {pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), pk2(q1.z, q1.w)};
 #pragma unroll
     for (int m = 0; m < MM; ++m) {
-      const float mean = s1[m] * (1.0f / kD);
+      const f32x2 nmean = pk2(s1[m] * (-1.0f / kD));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float x = d[m][hblk * 8 + k] - mean;
-        d[m][hblk * 8 + k] = x;
-        s2[m] = fmaf(x, x, s2[m]);
-        sq[m] = fmaf(x, gq[k], sq[m]);
+      for (int k = 0; k < 4; ++k) {
+        const f32x2 x = add2(d[m][hblk * 4 + k], nmean);
+        d[m][hblk * 4 + k] = x;
+        s2p[m] = fma2(x, x, s2p[m]);
+        sqp[m] = fma2(x, gq[k], sqp[m]);
       }
     }
+  }
+  float s2[MM], sq[MM];
+#pragma unroll
+  for (int m = 0; m < MM; ++m) {
+    float lo, hi;
+    upk2(s2p[m], lo, hi); s2[m] = lo + hi;
+    upk2(sqp[m], lo, hi); sq[m] = lo + hi;
   }
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) {
@@ -353,28 +366,28 @@ __global__ void __launch_bounds__(256) k_merge_fusion_h2(const MergeParams p) {
 #pragma unroll
   for (int m = 0; m < MM; ++m) { logit[m] = (m < p.M) ? __expf(logit[m] - mx) : 0.f; den += logit[m]; }
   const float inv_den = __fdividef(1.0f, den);
-  float wgt[MM];
+  f32x2 wgt[MM];
 #pragma unroll
   for (int m = 0; m < MM; ++m) {
     const float a = logit[m] * inv_den;
-    wgt[m] = a * sc[m];
+    wgt[m] = pk2(a * sc[m]);
     if (p.attn != nullptr && sub == 0 && live && m < p.M) p.attn[r * p.M + m] = a;
   }
 #pragma unroll
   for (int hblk = 0; hblk < 2; ++hblk) {
     const int c = hblk ? c1 : c0;
-    float mix[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float a = 0.f;
-#pragma unroll
-      for (int m = 0; m < MM; ++m) a = fmaf(wgt[m], d[m][hblk * 8 + k], a);
-      mix[k] = a;
-    }
     const float4 g0 = *reinterpret_cast<const float4*>(s_g + c), g1 = *reinterpret_cast<const float4*>(s_g + c + 4);
     const float4 b0 = *reinterpret_cast<const float4*>(s_b + c), b1 = *reinterpret_cast<const float4*>(s_b + c + 4);
-    mix[0] = fmaf(mix[0], g0.x, b0.x); mix[1] = fmaf(mix[1], g0.y, b0.y); mix[2] = fmaf(mix[2], g0.z, b0.z); mix[3] = fmaf(mix[3], g0.w, b0.w);
-    mix[4] = fmaf(mix[4], g1.x, b1.x); mix[5] = fmaf(mix[5], g1.y, b1.y); mix[6] = fmaf(mix[6], g1.z, b1.z); mix[7] = fmaf(mix[7], g1.w, b1.w);
+    const f32x2 g2[4] = {pk2(g0.x, g0.y), pk2(g0.z, g0.w), pk2(g1.x, g1.y), pk2(g1.z, g1.w)};
+    const f32x2 b2[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
+    float mix[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f32x2 a = mul2(wgt[0], d[0][hblk * 4 + k]);
+#pragma unroll
+      for (int m = 1; m < MM; ++m) a = fma2(wgt[m], d[m][hblk * 4 + k], a);
+      upk2(fma2(a, g2[k], b2[k]), mix[2 * k], mix[2 * k + 1]);
+    }
     if (live) Row8<__half>::store(reinterpret_cast<__half*>(p.mix) + r * kD + c, mix);
   }
 }

@@ -90,6 +90,16 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "l"(kEvictNormal)
       : "memory");
 }
+// ---- staging tile -> global through the TMA engine (one elected lane; the tile is a SWIZZLE_64B box of 32 rows x 64 bytes, which is
+// exactly the stg_addr layout below). Every lane fences its own st.shared to the async proxy before the warp elects the issuer.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

@@ -52,7 +52,7 @@ constexpr int RED_BYTES = EPI_WARPS * 32 * 8;              // (sum, sumsq) excha
 constexpr int MAX_FFN = 1024;
 constexpr int PAR_FLOATS = 6 * DM + MAX_FFN;               // bo, b2, ln1 gamma/beta, ln2 gamma/beta, b1
 constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES + RED_BYTES + PAR_FLOATS * 4 + 1024;
-constexpr int STG_WARP_BYTES = 32 * 64;
+constexpr int STG_WARP_BYTES = 2 * 32 * 64;            // two staging tiles per epilogue warp (TMA stores alternate between them)
 static_assert(EPI_WARPS * STG_WARP_BYTES <= 4 * SUB, "the epilogue staging tiles alias the h buffers");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 constexpr int TMEM_COLS = 512;
@@ -89,7 +89,8 @@ __device__ long long* g_tl_trace = nullptr;
 #endif
 
 __global__ void __launch_bounds__(THREADS, 1)
-k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
+k_tlayer_tail(const __grid_constant__ CUtensorMap map_x32, const __grid_constant__ CUtensorMap map_x16,
+              const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
               const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TlParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -295,9 +296,12 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
 #pragma unroll
         for (int u = 0; u < NCH; ++u)
           unit_load(reinterpret_cast<const char*>(p.x_in), (int64_t)DM * 4, rm, p.M, (int64_t)(nl + u * CW) * 4, lane, rres[u]);
+        TL_TRACE(1, 10);
         mbar_wait(bar(B_OFULL), (uint32_t)(it & 1));
         tc_fence_after();
         TL_TRACE(1, 1);
+        if (lane == 0) bulk_wait_read<0>();                  // LayerNorm2 of the previous tile: its TMA stores have read the staging tiles
+        __syncwarp();
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           unit_to_smem(stg, lane, rres[u]);
@@ -322,6 +326,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           __syncwarp();
         }
         tmem_st_wait();
+        TL_TRACE(1, 11);
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red0 + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
         float S1 = 0.f, S2 = 0.f;
@@ -336,6 +341,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
         const float var = fmaxf(S2 * (1.0f / DM) - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
+        TL_TRACE(1, 12);
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
           uint32_t raw[CW];
@@ -439,6 +445,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
           tmem_st16(t_o + (uint32_t)(u * CW), raw);
         }
         tmem_st_wait();
+        TL_TRACE(1, 91);
         const uint32_t red1 = red0;
         asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(red1 + (uint32_t)(((warp - 2) * 32 + lane) * 8)), "f"(s1), "f"(s2) : "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(4 * 32) : "memory");
@@ -454,6 +461,7 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
         const float var = fmaxf(S2 * (1.0f / DM) - mean * mean, 0.f);
         const float rstd = 1.0f / sqrtf(var + 1e-5f);
         const float nmr = -mean * rstd;
+        TL_TRACE(1, 92);
         uint32_t h16[CW];
 #pragma unroll
         for (int u = 0; u < NCH; ++u) {
@@ -471,30 +479,41 @@ k_tlayer_tail(const __grid_constant__ CUtensorMap map_att, const __grid_constant
             y[i + 2] = fmaf(fmaf(__uint_as_float(raw[i + 2]), rstd, nmr), g.z, b.z);
             y[i + 3] = fmaf(fmaf(__uint_as_float(raw[i + 3]), rstd, nmr), g.w, b.w);
           }
+          // fp32 stream: 16 columns x 32 rows = one staging tile, handed to the TMA engine by one lane. The six stores of a tile
+          // (u0, u1, fp16, u2, u3, fp16) alternate between the warp's two staging tiles: store n fills tile n & 1 once store n - 2
+          // has been read, i.e. with at most ONE store still pending
+          const int n32 = u + (u >= 2 ? 1 : 0);
+          const uint32_t st32 = stg + (uint32_t)((n32 & 1) * 2048);
+          if (n32 >= 1) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            sts128(stg_addr(stg, lane, i), make_uint4(__float_as_uint(y[i * 4]), __float_as_uint(y[i * 4 + 1]),
-                                                      __float_as_uint(y[i * 4 + 2]), __float_as_uint(y[i * 4 + 3])));
+            sts128(stg_addr(st32, lane, i), make_uint4(__float_as_uint(y[i * 4]), __float_as_uint(y[i * 4 + 1]),
+                                                       __float_as_uint(y[i * 4 + 2]), __float_as_uint(y[i * 4 + 3])));
 #pragma unroll
           for (int i = 0; i < CW / 2; ++i) {
             const __half2 t = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
             h16[(u & 1) * (CW / 2) + i] = *reinterpret_cast<const uint32_t*>(&t);
           }
+          fence_async_smem();
           __syncwarp();
-          unit_store(reinterpret_cast<char*>(p.x_out), (int64_t)DM * 4, rm, p.M, (int64_t)(nl + u * CW) * 4, lane, stg);
-          __syncwarp();
-          if (u & 1) {
+          if (lane == 0) { tma_store_2d(&map_x32, st32, nl + u * CW, (int)(m_tile * BM) + q * 32); bulk_commit(); }
+          if (u & 1) {                                         // fp16 copy of the last two units: 32 columns x 32 rows, into the OTHER tile
+            const uint32_t st16 = stg + (uint32_t)(((n32 + 1) & 1) * 2048);
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sts128(stg_addr(stg, lane, i), make_uint4(h16[i * 4], h16[i * 4 + 1], h16[i * 4 + 2], h16[i * 4 + 3]));
+            for (int i = 0; i < 4; ++i) sts128(stg_addr(st16, lane, i), make_uint4(h16[i * 4], h16[i * 4 + 1], h16[i * 4 + 2], h16[i * 4 + 3]));
+            fence_async_smem();
             __syncwarp();
-            unit_store(reinterpret_cast<char*>(p.x16_out), (int64_t)DM * 2, rm, p.M, (int64_t)(nl + (u - 1) * CW) * 2, lane, stg);
-            __syncwarp();
+            if (lane == 0) { tma_store_2d(&map_x16, st16, nl + (u - 1) * CW, (int)(m_tile * BM) + q * 32); bulk_commit(); }
           }
+          TL_TRACE(1, 93 + u);
         }
       }
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait<0>();                 // this warp's TMA stores have completed
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -534,8 +553,19 @@ cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(encode_fn);
-  CUtensorMap m_att, m_wo, m_w1, m_w2;
+  CUtensorMap m_att, m_wo, m_w1, m_w2, m_x32, m_x16;
   cuuint32_t es3[3] = {1, 1, 1}, es2[2] = {1, 1};
+  {
+    // outputs: the epilogue's staging tiles (32 rows x 64 bytes, SWIZZLE_64B) leave through TMA stores; rows past M are clipped
+    cuuint64_t gdim[2] = {(cuuint64_t)DM, (cuuint64_t)t.M}, s32[1] = {(cuuint64_t)DM * 4}, s16[1] = {(cuuint64_t)DM * 2};
+    cuuint32_t b32[2] = {16, 32}, b16[2] = {32, 32};
+    CUresult r = encode(&m_x32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, t.x32, gdim, s32, b32, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS)
+      r = encode(&m_x16, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, t.x16, gdim, s16, b16, es2, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(outputs) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
+  }
   {
     cuuint64_t gdim[3] = {(cuuint64_t)DM, (cuuint64_t)t.M, 1}, gstr[2] = {(cuuint64_t)DM * 2, (cuuint64_t)t.M * DM * 2};
     cuuint32_t box[3] = {BK, BM, 1};
@@ -569,7 +599,7 @@ cudaError_t launch_tlayer_tail(void* encode_fn, int num_sms, const TlayerTail& t
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_tlayer_tail, m_att, m_wo, m_w1, m_w2, p);
+  return cudaLaunchKernelEx(&cfg, k_tlayer_tail, m_x32, m_x16, m_att, m_wo, m_w1, m_w2, p);
 }
 
 #ifdef TAG_EXPERIMENTS
