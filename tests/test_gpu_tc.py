@@ -302,7 +302,7 @@ def test_product_library_ignores_experiment_switches():
     import os, subprocess, sys
     if os.environ.get("TAG_TC_DEBUG"):
         pytest.skip("inside the child")
-    env = dict(os.environ, TAG_TC_DEBUG="7", TAG_TC_HALO="3", TAG_K1_DEBUG="7", TAG_FRAME_TABLE="0", TAG_TC_PAIR="0")
+    env = dict(os.environ, TAG_TC_DEBUG="7", TAG_TC_HALO="3", TAG_K1_DEBUG="7", TAG_FRAME_TABLE="0", TAG_TC_PAIR="0", TAG_TC_TMA_STORE="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
                         "fused_pipeline_tc_scores"], env=env, capture_output=True, text=True, timeout=600,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
