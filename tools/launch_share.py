@@ -28,7 +28,7 @@ for _, n, t in step:
     agg[k][1] += t
 tot = sum(v[1] for v in agg.values())
 conv1 = [step[i][2] for i in range(len(step) - 1) if short(step[i][1]).startswith("k_gemm_tc<0") and short(step[i + 1][1]).startswith("k_gemm_tc<1")]
-gn = agg.get("k_gemm_tc<1, 1>", [0, 0.0])[1]
+gn = sum(v[1] for k, v in agg.items() if k.startswith("k_gemm_tc<1"))      # MODE 1 = conv2 + residual + GELU + GroupNorm
 print(f"{len(recs)} launches in the list; timed step: {len(step)} launches, {tot / 1e6:.2f} ms summed.\n")
 print("| kernel | launches | total ms | share | avg us |\n|---|---|---|---|---|")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):

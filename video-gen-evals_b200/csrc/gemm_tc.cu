@@ -460,7 +460,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const RowMap rm{m_tile * BLOCK_M, q * 32, p.lw, p.lt};   // this warp's 32 tile rows -> global rows
-      const bool my_row_valid = tile_row(rm.tile_base, rm.rt0 + lane, rm.lw, rm.lt) < p.M;
       const int n_base = n_tile * BLOCK_N + part * EPI_COLS;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + part * EPI_COLS);
       if constexpr (GN) {
@@ -484,10 +483,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
             tmem_ld16_wait(raw);
             float v[CW];
             epi_values<16, 1>(p, raw, stg, lane, cc * 2, v, n_base + c * CW);
-            if (!my_row_valid) {
-#pragma unroll
-              for (int i = 0; i < CW; ++i) v[i] = 0.f;
-            }
+            // rows past M need no masking: M is a whole number of windows and a tile owns whole windows, so such rows only feed the
+            // statistics of windows that are never stored (their activations are TMA zero fill, their residual reads return 0)
 #pragma unroll
             for (int i = 0; i < CW / 2; ++i) {
               const f32x2 vv = pk2(v[2 * i], v[2 * i + 1]);
