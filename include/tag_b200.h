@@ -224,6 +224,13 @@ int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x1
                           const void* W1_16, const void* W2_16, const float* bo, const float* b1, const float* b2,
                           const float* ln1_g, const float* ln1_b, const float* ln2_g, const float* ln2_b, void* stream);
 
+/* one fused TemporalConvBlock (model.py:22-41) in tensor-core mode: h16 <- GroupNorm(GELU(conv2(GELU(conv1(h16))) + h16)), in place,
+ * [M, 256] fp16 rows of whole windows (M = windows * T); weights fp16 [256, 5 * 256], tap-major K; no conv bias (as the reference).
+ * Returns TAG_ERR_UNSUPPORTED where the two-kernel path (tag_debug_gemm_tc twice) is used instead: T not a power of two <= 128, or a
+ * dilation whose halo tile does not fit next to the weight ring (T = 32: dilation 8). Bit-identical to that path. */
+int tag_debug_tcn_block(tag_handle* h, void* h16, int64_t M, int32_t T, int32_t dil, const void* W1_16, const void* W2_16,
+                        const float* gn_gamma, const float* gn_beta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtag_b200.so")
-SOURCES = ["tag_api.cu", "k1_feature_fuse.cu", "k34_score.cu", "enc_kernels.cu", "gemm_simt.cu", "gemm_tc.cu", "tlayer_tc.cu"]
+SOURCES = ["tag_api.cu", "k1_feature_fuse.cu", "k34_score.cu", "enc_kernels.cu", "gemm_simt.cu", "gemm_tc.cu", "tlayer_tc.cu", "tcn_block_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v"]
 

@@ -145,6 +145,21 @@ cudaError_t launch_gemm_tc(TcContext* ctx, const GemmTC& g, cudaStream_t s, char
 void* tc_encode_fn(const TcContext*);     // cuTensorMapEncodeTiled entry point
 int tc_num_sms(const TcContext*);
 
+// ------------------------------------------------------------------ fused TemporalConvBlock (tcn_block_tc.cu)
+// h <- GroupNorm(GELU(conv2(GELU(conv1(h) + b1)) + b2 + h)) for [M, 256] fp16 rows of whole windows (M = windows * T), in place; the
+// intermediate activation never leaves shared memory. Bit-identical to conv1 + GELU followed by conv2 + residual + GELU + GroupNorm
+// through launch_gemm_tc. tcn_block_supported(): T a power of two <= 128 and a dilation whose halo tile fits next to the weight ring.
+struct TcnBlock {
+  int64_t M; int T; int dil;
+  __half* h16;                    // [M,256] block input = residual = output
+  const __half* W1_16;            // [256, 5*256] tap-major K
+  const __half* W2_16;
+  const float* b1; const float* b2;   // conv biases or null (the reference's convs have none)
+  const float* gn_gamma; const float* gn_beta;
+};
+bool tcn_block_supported(int64_t M, int T, int dil);
+cudaError_t launch_tcn_block(void* encode_fn, int num_sms, const TcnBlock& t, cudaStream_t s, char* err, int errlen);
+
 // ------------------------------------------------------------------ fused transformer-layer tail (tlayer_tc.cu)
 // x <- LN2(x1 + relu(x1 W1^T + b1) W2^T + b2), x1 = LN1(x + att Wo^T + bo): out-proj + norm1 + FFN + norm2 of one post-norm
 // layer (model.py:145) in one tcgen05 kernel; x32 is updated in place, x16 receives its fp16 copy

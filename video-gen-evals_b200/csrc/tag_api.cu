@@ -88,6 +88,7 @@ struct tag_handle {
   int32_t* zeros = nullptr;         // [max_windows] 0
   int32_t *clip_wv = nullptr, *clip_ws = nullptr;   // [max_windows] window table of one pass (fallback path)
   float* row0 = nullptr;            // [M][256]: motion stem applied to the z-scored zero difference
+  int fuse_tcn = 1;                 // fused TemporalConvBlock kernel where it fits (TAG_FUSE_TCN=0: conv1 and conv2 + GroupNorm as two GEMM launches)
   int fuse_tail = 1;                // fused transformer-layer tail (TAG_FUSE_TAIL=0 selects the three separate GEMMs in TAG_EXPERIMENTS builds)
   int frame_table = 1;              // frame-table mode of tag_encode_clips (TAG_FRAME_TABLE=0 disables it in TAG_EXPERIMENTS builds)
   float* attn_out = nullptr;        // tag_set_fusion_attn_out: [rows, M] fusion softmax of the NEXT tag_encode call (model.py:94 last_attn)
@@ -352,6 +353,21 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
       }
       rc = gemm_tc_run(h, s, g, 2.0 * R * kD * e.d_in); if (rc) return rc;
       for (int b = 0; b < h->cfg.n_blocks; ++b) {
+        if (h->fuse_tcn && kk == 5 && tc_pair_enabled(h->tc) && tcn_block_supported(R, T, 1 << b)) {
+          // the whole TemporalConvBlock in ONE kernel (tcn_block_tc.cu): GELU(conv1) stays in shared memory as conv2's operand
+          TcnBlock tb{};
+          tb.M = R; tb.T = T; tb.dil = 1 << b; tb.h16 = bufH; tb.W1_16 = e.conv16[b][0]; tb.W2_16 = e.conv16[b][1];
+          tb.gn_gamma = e.gn_g[b]; tb.gn_beta = e.gn_b[b];
+          ProfScope ps(h, s, 1, 2.0 * (2.0 * R * kD * kD * kk));
+          h->err[0] = 0;
+          cudaError_t ce = launch_tcn_block(tc_encode_fn(h->tc), tc_num_sms(h->tc), tb, s, h->err, 512);
+          h->launches++;
+          if (ce != cudaSuccess) {
+            if (h->err[0] == 0) fail(h, TAG_ERR_CUDA, "tcn_block launch failed: %s", cudaGetErrorString(ce));
+            return TAG_ERR_CUDA;
+          }
+          continue;
+        }
         GemmTC c1{};
         c1.A = bufH; c1.M = R; c1.lda = kD; c1.W = e.conv16[b][0]; c1.N = kD; c1.K = kD; c1.taps = kk; c1.dil = 1 << b;
         c1.T = T; c1.C16 = bufY1; c1.ldc = kD; c1.act = 1;
@@ -802,6 +818,8 @@ int tag_finalize_weights(tag_handle* h) {
     if (env != nullptr) h->frame_table = atoi(env);
     env = getenv("TAG_FUSE_TAIL");
     if (env != nullptr) h->fuse_tail = atoi(env);
+    env = getenv("TAG_FUSE_TCN");
+    if (env != nullptr) h->fuse_tcn = atoi(env);
 #endif
   } else {
     if ((rc = dev_alloc(h, &h->feats, R * h->D))) return rc;
@@ -1170,6 +1188,28 @@ int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x1
   h->launches++;
   if (e != cudaSuccess) {
     if (h->err[0] == 0) fail(h, TAG_ERR_CUDA, "tlayer_tail launch failed: %s", cudaGetErrorString(e));
+    return e == cudaErrorInvalidValue ? TAG_ERR_INVALID : TAG_ERR_CUDA;
+  }
+  return TAG_OK;
+}
+
+int tag_debug_tcn_block(tag_handle* h, void* h16, int64_t M, int32_t T, int32_t dil, const void* W1_16, const void* W2_16,
+                        const float* gn_gamma, const float* gn_beta, void* stream) {
+  if (!h) return TAG_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  if (!h->tc) {
+    h->tc = tc_context_create(h->cfg.device, h->err, 512);
+    if (!h->tc) return TAG_ERR_CUDA;
+  }
+  if (!tcn_block_supported(M, T, dil)) return fail(h, TAG_ERR_UNSUPPORTED, "tcn_block: shape not supported (M=%lld T=%d dil=%d)", (long long)M, T, dil);
+  TcnBlock tb{};
+  tb.M = M; tb.T = T; tb.dil = dil; tb.h16 = (__half*)h16; tb.W1_16 = (const __half*)W1_16; tb.W2_16 = (const __half*)W2_16;
+  tb.gn_gamma = gn_gamma; tb.gn_beta = gn_beta;
+  h->err[0] = 0;
+  cudaError_t e = launch_tcn_block(tc_encode_fn(h->tc), tc_num_sms(h->tc), tb, (cudaStream_t)stream, h->err, 512);
+  h->launches++;
+  if (e != cudaSuccess) {
+    if (h->err[0] == 0) fail(h, TAG_ERR_CUDA, "tcn_block launch failed: %s", cudaGetErrorString(e));
     return e == cudaErrorInvalidValue ? TAG_ERR_INVALID : TAG_ERR_CUDA;
   }
   return TAG_OK;
