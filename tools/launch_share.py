@@ -33,11 +33,13 @@ print(f"{len(recs)} launches in the list; timed step: {len(step)} launches, {tot
 print("| kernel | launches | total ms | share | avg us |\n|---|---|---|---|---|")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{k}` | {v[0]} | {v[1] / 1e6:.3f} | {v[1] / tot * 100:.1f} % | {v[1] / v[0] / 1e3:.1f} |")
-print(f"\nconv1 launches (the `<0,1>` launch right before each `<1,1>`): {len(conv1)}, {sum(conv1) / 1e6:.2f} ms = {sum(conv1) / tot * 100:.1f} %; "
-      f"dilated-conv GEMMs together {(sum(conv1) + gn) / 1e6:.2f} ms = **{(sum(conv1) + gn) / tot * 100:.1f} % of the step**.")
+blk = sum(v[1] for k, v in agg.items() if k.startswith("k_tcn_block"))      # fused TemporalConvBlock launches (conv1 + conv2 + GroupNorm)
+print(f"\nfused TemporalConvBlock launches: {blk / 1e6:.2f} ms; conv1 launches of the two-kernel blocks (the `<0,1>` launch right before each `<1,1>`): "
+      f"{len(conv1)}, {sum(conv1) / 1e6:.2f} ms; conv2 + GroupNorm launches {gn / 1e6:.2f} ms; "
+      f"dilated-conv work together {(blk + sum(conv1) + gn) / 1e6:.2f} ms = **{(blk + sum(conv1) + gn) / tot * 100:.1f} % of the step**.")
 gem = sum(v[1] for k, v in agg.items() if k.startswith("k_gemm_tc") or k.startswith("k_tlayer_tail")) - sum(conv1) - gn
 k1t = sum(v[1] for k, v in agg.items() if "feature_fuse" in k)
-oth = tot - gem - sum(conv1) - gn - k1t
+oth = tot - gem - sum(conv1) - gn - blk - k1t
 print(f"other GEMMs {gem / tot * 100:.1f} %, K1 {k1t / tot * 100:.1f} %, other kernels {oth / tot * 100:.1f} %.")
 if len(sys.argv) > 2:
     d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])

@@ -148,13 +148,12 @@ int tc_num_sms(const TcContext*);
 // ------------------------------------------------------------------ fused TemporalConvBlock (tcn_block_tc.cu)
 // h <- GroupNorm(GELU(conv2(GELU(conv1(h) + b1)) + b2 + h)) for [M, 256] fp16 rows of whole windows (M = windows * T), in place; the
 // intermediate activation never leaves shared memory. Bit-identical to conv1 + GELU followed by conv2 + residual + GELU + GroupNorm
-// through launch_gemm_tc. tcn_block_supported(): T a power of two <= 128 and a dilation whose halo tile fits next to the weight ring.
+// through launch_gemm_tc. tcn_block_supported(): T a power of two <= 128, more than 128 rows, and a dilation whose halo tiles leave room for three weight stages.
 struct TcnBlock {
   int64_t M; int T; int dil;
   __half* h16;                    // [M,256] block input = residual = output
   const __half* W1_16;            // [256, 5*256] tap-major K
   const __half* W2_16;
-  const float* b1; const float* b2;   // conv biases or null (the reference's convs have none)
   const float* gn_gamma; const float* gn_beta;
 };
 bool tcn_block_supported(int64_t M, int T, int dil);

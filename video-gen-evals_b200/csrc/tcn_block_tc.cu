@@ -1,7 +1,7 @@
 // Fused TemporalConvBlock (reference model.py:22-41) for the tensor-core encoder: ONE persistent cta_group::2 tcgen05 kernel per block
 //
-//   y1 = GELU(conv1(h) + b1)                       (dilated conv, 5 taps, 256 -> 256 channels)
-//   h  = GroupNorm_1(GELU(conv2(y1) + b2 + h))     (same shape; one group over the whole (T x 256) window)
+//   y1 = GELU(conv1(h))                            (dilated conv, 5 taps, 256 -> 256 channels, no bias)
+//   h  = GroupNorm_1(GELU(conv2(y1) + h))          (same shape; one group over the whole (T x 256) window)
 //
 // The two-kernel path (gemm_tc.cu: conv1 + GELU, then conv2 + residual + GELU + GroupNorm) writes y1 to HBM (fp16) and reads it back
 // as the activation operand of conv2: 410 MB of the 936 MB a block moves per 400,000 rows, and — measured with the load / store
@@ -15,13 +15,13 @@
 //   warp 0   TMA producer: 4 x (h chunk with its time halo + 5 W1 tap tiles), then 4 x 5 W2 tap tiles, in consumption order
 //   warp 1   MMA issuer (leader CTA): conv1 into TMEM columns 0-255; conv2 into columns 256-511, chunk by chunk as the epilogue
 //            hands over the 64-channel sub-tiles of y1
-//   warps 2-17  epilogue: (1) conv1 accumulator -> +b1 -> GELU -> fp16 -> y1 sub-tiles (every warp takes a 16-channel slice of EVERY
+//   warps 2-17  epilogue: (1) conv1 accumulator -> GELU -> fp16 -> y1 sub-tiles (every warp takes a 16-channel slice of EVERY
 //            sub-tile, so sub-tile 0 is complete after a quarter of this phase and conv2 starts then); (2) conv2 accumulator ->
-//            +b2 + residual -> GELU -> GroupNorm -> fp16 -> TMA stores, exactly as MODE 1 of gemm_tc.cu. Phase (2) of tile i runs
+//            + residual -> GELU -> GroupNorm -> fp16 -> TMA stores, exactly as MODE 1 of gemm_tc.cu. Phase (2) of tile i runs
 //            under conv1 of tile i + 1.
-// Shared memory: y1 (4 sub-tiles of (T + 4 dil) NW rows x 128 B) | 2 activation chunks | weight ring | barriers, GroupNorm exchange,
-// gamma / beta, biases. The epilogue's staging tiles alias the interior rows of the y1 sub-tiles (dead while phase (2) runs).
-// Fits for dilations whose halo keeps y1 + the activation ring under ~150 KB (T = 32: dil 1, 2, 4); other blocks take the two-kernel path.
+// Shared memory: y1 (4 sub-tiles of 128 rows x 128 B between shared zero halos of 2 dil NW rows) | 2 activation chunks | weight ring
+// (7 / 6 / 5 stages for dilation 1 / 2 / 4 at T = 32; dilation 8 would leave 3 and stays on the two-kernel path) | barriers, GroupNorm
+// exchange, gamma / beta. The epilogue's staging tiles alias the interior rows of the y1 sub-tiles (dead while phase (2) runs).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -42,8 +42,9 @@ constexpr int EPI_WARPS = 16, THREADS = 64 + EPI_WARPS * 32, CW = 16;
 constexpr int B_BYTES = (BN / 2) * BK * 2;                       // 16 KiB: this CTA's half of a weight tap tile
 constexpr int MAX_B = 8, N_A = 2;
 constexpr int BAR_BYTES = 512;
-constexpr int GN_RED_BYTES = 2 * EPI_WARPS * 32 * 8;             // double-buffered per-lane (sum, sumsq) exchange
-constexpr int PAR_BYTES = 4 * BN * 4;                            // gamma | beta | b1 | b2
+constexpr int GN_RED_BYTES = EPI_WARPS * 32 * 8;                 // per-lane (sum, sumsq) exchange. One buffer: between reading it for tile i and
+                                                                 // writing it for tile i + 1 every warp passes the bar.sync of phase (1)
+constexpr int PAR_BYTES = 2 * BN * 4;                            // gamma | beta (the reference's convs have no bias, model.py:25-29)
 constexpr int STG_TILE = 32 * 64;                                // per-warp staging tile (32 rows x 64 B, SWIZZLE_64B)
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 constexpr int TMEM_COLS = 512;
@@ -56,8 +57,10 @@ struct TbParams {
   int64_t M, m_tiles;
   int T, lw, lt, nw;            // frames per window, log2(windows per tile), log2(frames per window), windows per tile
   int dil, tap_rows, halo_rows; // rows of one tap shift (dil * nw), zero rows on each side (2 * dil * nw)
-  int y_sub_bytes, a_stage_bytes, a_box_bytes, stg_off, b_stages;
-  const float* b1; const float* b2; const float* gn_gamma; const float* gn_beta;
+  int y_sub_bytes;              // distance of the y1 sub-tiles: (halo + 128) rows when consecutive sub-tiles share a zero halo, else (2 halo + 128)
+  int y_bytes;                  // all of y1
+  int a_stage_bytes, a_box_bytes, stg_off, b_stages;
+  const float* gn_gamma; const float* gn_beta;
   const __half* res16; int ldr;
 };
 
@@ -67,24 +70,22 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t y1 = smem_base;
-  const uint32_t a_ring = y1 + (uint32_t)(KC * p.y_sub_bytes);
+  const uint32_t a_ring = y1 + (uint32_t)p.y_bytes;
   const uint32_t b_ring = a_ring + (uint32_t)(N_A * p.a_stage_bytes);
   const uint32_t bar_base = b_ring + (uint32_t)(p.b_stages * B_BYTES);
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bar_base + 8u * N_BARS;
   const uint32_t red_base = bar_base + BAR_BYTES;
-  float* s_par = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES + GN_RED_BYTES);   // gamma | beta | b1 | b2
+  float* s_par = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + BAR_BYTES + GN_RED_BYTES);   // gamma | beta
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   for (int i = threadIdx.x; i < BN; i += THREADS) {
     s_par[i] = __ldg(p.gn_gamma + i); s_par[BN + i] = __ldg(p.gn_beta + i);
-    s_par[2 * BN + i] = p.b1 != nullptr ? __ldg(p.b1 + i) : 0.f;      // the reference's convs have no bias (model.py:25-29): zeros
-    s_par[3 * BN + i] = p.b2 != nullptr ? __ldg(p.b2 + i) : 0.f;
   }
   // y1: everything zero once; the epilogue only ever writes the 128 interior rows of a sub-tile (and its staging tiles live there)
-  for (int i = threadIdx.x; i < KC * p.y_sub_bytes / 16; i += THREADS) sts128(y1 + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
+  for (int i = threadIdx.x; i < p.y_bytes / 16; i += THREADS) sts128(y1 + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_B; ++s) { mbar_init(bar(B_FULLB + s), 1); mbar_init(bar(B_EMPTYB + s), 1); }
@@ -198,7 +199,7 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
       const int64_t m_tile = tile * 2 + rank;
       const uint32_t par = (uint32_t)(it & 1);
       const RowMap rm{m_tile * BM, q * 32, p.lw, p.lt};
-      // ---------------- phase (1): y1 = GELU(acc1 + b1) -> fp16 -> shared memory
+      // ---------------- phase (1): y1 = GELU(acc1) -> fp16 -> shared memory
       mbar_wait(bar(B_ACC1F), par);
       tc_fence_after();
       // the staging tiles of the previous tile's phase (2) live inside y1: every warp's TMA stores must have read theirs
@@ -209,14 +210,12 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
         uint32_t raw[CW];
         tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kc * BK + part * CW), raw);
         tmem_ld16_wait(raw);
-        const float* bb = s_par + 2 * BN + kc * BK + part * CW;
         uint4 o[2];
         __half2* hh = reinterpret_cast<__half2*>(o);
 #pragma unroll
         for (int i = 0; i < CW / 2; ++i) {
-          const float2 b = *reinterpret_cast<const float2*>(bb + 2 * i);
           float v0, v1;
-          upk2(gelu_fast2(add2(pk2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1])), pk2(b.x, b.y))), v0, v1);
+          upk2(gelu_fast2(pk2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]))), v0, v1);
           hh[i] = __floats2half2_rn(v0, v1);
         }
         const uint32_t dst = y_row + (uint32_t)(kc * p.y_sub_bytes);
@@ -230,7 +229,7 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
           if (kc == KC - 1) mbar_arrive_leader(bar(B_ACC1E));
         }
       }
-      // ---------------- phase (2): GroupNorm(GELU(acc2 + b2 + h)) -> fp16 -> TMA stores (as MODE 1 of gemm_tc.cu, halo tiles)
+      // ---------------- phase (2): GroupNorm(GELU(acc2 + h)) -> fp16 -> TMA stores (as MODE 1 of gemm_tc.cu, halo tiles)
       {
         const int n_base = part * 64;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + n_base);
@@ -251,13 +250,9 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
             uint32_t raw[CW];
             tmem_ld16_issue(t_row + (uint32_t)(c * CW), raw);
             tmem_ld16_wait(raw);
-            const float* bb = s_par + 3 * BN + n_base + c * CW;
             f32x2 w[CW / 2];
 #pragma unroll
-            for (int i = 0; i < CW / 2; ++i) {
-              const float2 b = *reinterpret_cast<const float2*>(bb + 2 * i);
-              w[i] = add2(pk2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1])), pk2(b.x, b.y));
-            }
+            for (int i = 0; i < CW / 2; ++i) w[i] = pk2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1]));
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const uint4 r = lds128(stg_addr(stg, lane, cc * 2 + i));
@@ -284,7 +279,7 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
         float s1, s2;
         { float a, b; upk2(s1p, a, b); s1 = a + b; upk2(s2p, a, b); s2 = a + b; }
         // window statistics: lane l of EVERY epilogue warp holds rows of window l & (NW-1)
-        const uint32_t red = red_base + (uint32_t)((it & 1) * EPI_WARPS * 32 * 8);
+        const uint32_t red = red_base;
         for (int o = 16; o >= p.nw; o >>= 1) {
           s1 += __shfl_xor_sync(FULL_MASK, s1, o);
           s2 += __shfl_xor_sync(FULL_MASK, s2, o);
@@ -357,7 +352,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct Plan { int nw, lw, lt, halo_rows, y_rows, y_sub, a_stage, stg_off, b_stages, smem; bool ok; };
+struct Plan { int nw, lw, lt, halo_rows, y_rows, y_sub, y_bytes, a_stage, stg_off, b_stages, smem; bool ok; };
 
 Plan make_plan(int64_t M, int T, int dil) {
   Plan pl{};
@@ -370,16 +365,20 @@ Plan make_plan(int64_t M, int T, int dil) {
   pl.halo_rows = 2 * dil * pl.nw;
   pl.y_rows = BM + 2 * pl.halo_rows;
   if (T + 4 * dil > 256) return pl;                              // TMA box limit of the activation chunk
-  pl.y_sub = (pl.y_rows * 128 + 1023) & ~1023;
-  pl.a_stage = pl.y_sub;                                         // same rows: an h chunk with its halo
+  pl.a_stage = (pl.y_rows * 128 + 1023) & ~1023;                 // an h chunk with its halo
+  // y1: the zero rows behind sub-tile k double as the zero rows in front of sub-tile k + 1 when that keeps every sub-tile on a
+  // 1024-byte boundary (the 128-byte swizzle pattern is a function of the address)
+  if (pl.halo_rows % 8 == 0) { pl.y_sub = (pl.halo_rows + BM) * 128; pl.y_bytes = KC * pl.y_sub + pl.halo_rows * 128; }
+  else { pl.y_sub = pl.a_stage; pl.y_bytes = KC * pl.y_sub; }
+  pl.y_bytes = (pl.y_bytes + 1023) & ~1023;
   pl.stg_off = (pl.halo_rows * 128 + 511) & ~511;                // staging tiles start inside the interior rows, 512-byte aligned
   if (pl.stg_off + 4 * STG_TILE > (pl.halo_rows + BM) * 128) return pl;
   const int fixed = 1024 + BAR_BYTES + GN_RED_BYTES + PAR_BYTES;
-  const int left = 232448 - fixed - KC * pl.y_sub - N_A * pl.a_stage;
+  const int left = 232448 - fixed - pl.y_bytes - N_A * pl.a_stage;
   pl.b_stages = left / B_BYTES;
   if (pl.b_stages > MAX_B) pl.b_stages = MAX_B;
-  if (pl.b_stages < 4) return pl;                                // fewer than 4 weight stages starve the mainloop (profiles/r2_conv_bstages_probe.log)
-  pl.smem = fixed + KC * pl.y_sub + N_A * pl.a_stage + pl.b_stages * B_BYTES;
+  if (pl.b_stages < 4) return pl;                                // T = 32, dilation 8 would get 3: measured 7 % SLOWER than the two GEMM launches (profiles/r2_tcn_block_micro.log)
+  pl.smem = fixed + pl.y_bytes + N_A * pl.a_stage + pl.b_stages * B_BYTES;
   pl.ok = true;
   return pl;
 }
@@ -441,8 +440,8 @@ cudaError_t launch_tcn_block(void* encode_fn, int num_sms, const TcnBlock& t, cu
   p.M = t.M; p.m_tiles = (t.M + BM - 1) / BM;
   p.T = t.T; p.lw = pl.nw > 1 ? pl.lw : 0; p.lt = pl.lt; p.nw = pl.nw;
   p.dil = t.dil; p.tap_rows = t.dil * pl.nw; p.halo_rows = pl.halo_rows;
-  p.y_sub_bytes = pl.y_sub; p.a_stage_bytes = pl.a_stage; p.a_box_bytes = pl.y_rows * 128; p.stg_off = pl.stg_off; p.b_stages = pl.b_stages;
-  p.b1 = t.b1; p.b2 = t.b2; p.gn_gamma = t.gn_gamma; p.gn_beta = t.gn_beta; p.res16 = t.h16; p.ldr = BN;
+  p.y_sub_bytes = pl.y_sub; p.y_bytes = pl.y_bytes; p.a_stage_bytes = pl.a_stage; p.a_box_bytes = pl.y_rows * 128; p.stg_off = pl.stg_off; p.b_stages = pl.b_stages;
+  p.gn_gamma = t.gn_gamma; p.gn_beta = t.gn_beta; p.res16 = t.h16; p.ldr = BN;
   const int64_t total = (p.m_tiles + 1) / 2;
   const int64_t clusters = total < num_sms / 2 ? total : num_sms / 2;
   cudaLaunchConfig_t cfg{};
