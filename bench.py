@@ -578,7 +578,7 @@ def main():
             "config": cfg,
             "precision": "fp16 operands, fp32 accumulate/norms (tcgen05)" if tc_mode else "fp32 CUDA cores",
             "windows_per_pass": max_windows,
-            "roofline": {"bound": "tensor", "kernel": "k_gemm_tc (dilated conv, 5 taps)" if tc_mode else "k_gemm_f32 (dilated conv, 5 taps)",
+            "roofline": {"bound": "tensor", "kernel": "k_tcn_block / k_gemm_tc (dilated-conv blocks, 5 taps: fused block kernel at dilation 1/2/4, two GEMM launches at dilation 8)" if tc_mode else "k_gemm_f32 (dilated conv, 5 taps)",
                          "achieved": achieved, "peak": roof_peak, "unit": "TFLOP/s",
                          "frac": (achieved / roof_peak) if achieved else None, "traffic": traffic,
                          "peak_source": pk["source"] if tc_mode else "nominal fp32 CUDA-core peak (~75 TFLOP/s), fp32 mode only",
