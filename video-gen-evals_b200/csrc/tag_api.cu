@@ -353,7 +353,7 @@ int encode_chunk_tc(tag_handle* h, cudaStream_t s, const __half* feats16, int64_
       }
       rc = gemm_tc_run(h, s, g, 2.0 * R * kD * e.d_in); if (rc) return rc;
       for (int b = 0; b < h->cfg.n_blocks; ++b) {
-        if (h->fuse_tcn && kk == 5 && tc_pair_enabled(h->tc) && tcn_block_supported(R, T, 1 << b)) {
+        if (h->fuse_tcn && !(h->fuse_tcn == 2 && b >= 3) && kk == 5 && tc_pair_enabled(h->tc) && tcn_block_supported(R, T, 1 << b)) {   // 2: A/B switch of the experiments build (dilation >= 8 unfused)
           // the whole TemporalConvBlock in ONE kernel (tcn_block_tc.cu): GELU(conv1) stays in shared memory as conv2's operand
           TcnBlock tb{};
           tb.M = R; tb.T = T; tb.dil = 1 << b; tb.h16 = bufH; tb.W1_16 = e.conv16[b][0]; tb.W2_16 = e.conv16[b][1];

@@ -19,9 +19,8 @@
 //            sub-tile, so sub-tile 0 is complete after a quarter of this phase and conv2 starts then); (2) conv2 accumulator ->
 //            + residual -> GELU -> GroupNorm -> fp16 -> TMA stores, exactly as MODE 1 of gemm_tc.cu. Phase (2) of tile i runs
 //            under conv1 of tile i + 1.
-// Shared memory: y1 (4 sub-tiles of 128 rows x 128 B between shared zero halos of 2 dil NW rows) | 2 activation chunks | weight ring
-// (7 / 6 / 5 stages for dilation 1 / 2 / 4 at T = 32; dilation 8 would leave 3 and stays on the two-kernel path) | barriers, GroupNorm
-// exchange, gamma / beta. The epilogue's staging tiles alias the interior rows of the y1 sub-tiles (dead while phase (2) runs).
+// Shared memory: six 128-row tiles (the 4 sub-tiles of y1, 2 activation stages) between shared zero halos of 2 dil NW rows | weight ring
+// (7 / 6 / 5 / 4 stages for dilation 1 / 2 / 4 / 8 at T = 32) | barriers, GroupNorm exchange, gamma / beta. The epilogue's staging tiles alias the interior rows of the y1 sub-tiles (dead while phase (2) runs).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -58,7 +57,10 @@ struct TbParams {
   int T, lw, lt, nw;            // frames per window, log2(windows per tile), log2(frames per window), windows per tile
   int dil, tap_rows, halo_rows; // rows of one tap shift (dil * nw), zero rows on each side (2 * dil * nw)
   int y_sub_bytes;              // distance of the y1 sub-tiles: (halo + 128) rows when consecutive sub-tiles share a zero halo, else (2 halo + 128)
-  int y_bytes;                  // all of y1
+  int a_ring_off;               // first activation stage (from the start of y1); the stages are a_stage_bytes apart
+  int a_dst_off, a_ct;          // where the TMA box lands inside a stage / its first frame: (halo rows, frame 0) in the compact layout — the
+                                // zero halos are never written — or (0, -2 dil) with TMA's out-of-bounds zero fill supplying them
+  int tiles_bytes;              // y1 + activation stages (zeroed once at kernel start)
   int a_stage_bytes, a_box_bytes, stg_off, b_stages;
   const float* gn_gamma; const float* gn_beta;
   const __half* res16; int ldr;
@@ -70,8 +72,8 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t y1 = smem_base;
-  const uint32_t a_ring = y1 + (uint32_t)p.y_bytes;
-  const uint32_t b_ring = a_ring + (uint32_t)(N_A * p.a_stage_bytes);
+  const uint32_t a_ring = y1 + (uint32_t)p.a_ring_off;
+  const uint32_t b_ring = y1 + (uint32_t)p.tiles_bytes;
   const uint32_t bar_base = b_ring + (uint32_t)(p.b_stages * B_BYTES);
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
   const uint32_t tmem_slot = bar_base + 8u * N_BARS;
@@ -85,7 +87,7 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
     s_par[i] = __ldg(p.gn_gamma + i); s_par[BN + i] = __ldg(p.gn_beta + i);
   }
   // y1: everything zero once; the epilogue only ever writes the 128 interior rows of a sub-tile (and its staging tiles live there)
-  for (int i = threadIdx.x; i < p.y_bytes / 16; i += THREADS) sts128(y1 + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
+  for (int i = threadIdx.x; i < p.tiles_bytes / 16; i += THREADS) sts128(y1 + (uint32_t)i * 16u, make_uint4(0u, 0u, 0u, 0u));
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_B; ++s) { mbar_init(bar(B_FULLB + s), 1); mbar_init(bar(B_EMPTYB + s), 1); }
@@ -108,7 +110,6 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
 
   const int64_t total_tiles = (p.m_tiles + 1) / 2;
   const int64_t tile0 = (int64_t)(blockIdx.x >> 1), tile_step = (int64_t)(gridDim.x >> 1);
-  const int pad = 2 * p.dil;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -125,7 +126,7 @@ k_tcn_block(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ C
         const int64_t m_tile = tile * 2 + rank;
         mbar_wait(bar(B_EMPTYA + sa), pa ^ 1u);
         if (leader) mbar_arrive_expect_tx(bar(B_FULLA + sa), 2u * (uint32_t)p.a_box_bytes);
-        tma_load_3d_pair(a_ring + (uint32_t)(sa * p.a_stage_bytes), &map_h, bar(B_FULLA + sa), kc * BK, (int)(m_tile * p.nw), -pad);
+        tma_load_3d_pair(a_ring + (uint32_t)(sa * p.a_stage_bytes + p.a_dst_off), &map_h, bar(B_FULLA + sa), kc * BK, (int)(m_tile * p.nw), p.a_ct);
         if (++sa == N_A) { sa = 0; pa ^= 1u; }
       };
       bool prefetched = false;                                // chunks 0 and 1 of `tile` were issued before the previous tile's W2 tiles
@@ -352,7 +353,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct Plan { int nw, lw, lt, halo_rows, y_rows, y_sub, y_bytes, a_stage, stg_off, b_stages, smem; bool ok; };
+struct Plan { int nw, lw, lt, halo_rows, y_sub, a_ring_off, a_stage, a_dst_off, a_ct, a_box_rows, tiles_bytes, stg_off, b_stages, smem; bool ok; };
 
 Plan make_plan(int64_t M, int T, int dil) {
   Plan pl{};
@@ -363,22 +364,34 @@ Plan make_plan(int64_t M, int T, int dil) {
   while ((1 << pl.lw) < pl.nw) ++pl.lw;
   while ((1 << pl.lt) < T) ++pl.lt;
   pl.halo_rows = 2 * dil * pl.nw;
-  pl.y_rows = BM + 2 * pl.halo_rows;
   if (T + 4 * dil > 256) return pl;                              // TMA box limit of the activation chunk
-  pl.a_stage = (pl.y_rows * 128 + 1023) & ~1023;                 // an h chunk with its halo
-  // y1: the zero rows behind sub-tile k double as the zero rows in front of sub-tile k + 1 when that keeps every sub-tile on a
-  // 1024-byte boundary (the 128-byte swizzle pattern is a function of the address)
-  if (pl.halo_rows % 8 == 0) { pl.y_sub = (pl.halo_rows + BM) * 128; pl.y_bytes = KC * pl.y_sub + pl.halo_rows * 128; }
-  else { pl.y_sub = pl.a_stage; pl.y_bytes = KC * pl.y_sub; }
-  pl.y_bytes = (pl.y_bytes + 1023) & ~1023;
+  if (pl.halo_rows % 8 == 0) {
+    // compact layout: six 128-row tiles (four y1 sub-tiles, two activation stages) separated by ONE zero halo each — the rows behind
+    // a tile double as the rows in front of the next; every tile stays on a 1024-byte boundary (the 128-byte swizzle pattern is a
+    // function of the address). The activation box covers frames 0 .. T-1 only and lands behind the stage's leading halo.
+    pl.y_sub = (pl.halo_rows + BM) * 128;
+    pl.a_stage = pl.y_sub;
+    pl.a_ring_off = KC * pl.y_sub;
+    pl.a_dst_off = pl.halo_rows * 128; pl.a_ct = 0; pl.a_box_rows = BM;
+    pl.tiles_bytes = (KC + N_A) * pl.y_sub + pl.halo_rows * 128;
+  } else {
+    // halo rows not a multiple of 8 (T = 128, dilation 1 .. 3): every tile carries both of its halos; the activation box starts at
+    // frame -2 dil and TMA's out-of-bounds zero fill writes the halo rows
+    pl.y_sub = ((BM + 2 * pl.halo_rows) * 128 + 1023) & ~1023;
+    pl.a_stage = pl.y_sub;
+    pl.a_ring_off = KC * pl.y_sub;
+    pl.a_dst_off = 0; pl.a_ct = -2 * dil; pl.a_box_rows = BM + 2 * pl.halo_rows;
+    pl.tiles_bytes = (KC + N_A) * pl.y_sub;
+  }
+  pl.tiles_bytes = (pl.tiles_bytes + 1023) & ~1023;
   pl.stg_off = (pl.halo_rows * 128 + 511) & ~511;                // staging tiles start inside the interior rows, 512-byte aligned
   if (pl.stg_off + 4 * STG_TILE > (pl.halo_rows + BM) * 128) return pl;
   const int fixed = 1024 + BAR_BYTES + GN_RED_BYTES + PAR_BYTES;
-  const int left = 232448 - fixed - pl.y_bytes - N_A * pl.a_stage;
+  const int left = 232448 - fixed - pl.tiles_bytes;
   pl.b_stages = left / B_BYTES;
   if (pl.b_stages > MAX_B) pl.b_stages = MAX_B;
-  if (pl.b_stages < 4) return pl;                                // T = 32, dilation 8 would get 3: measured 7 % SLOWER than the two GEMM launches (profiles/r2_tcn_block_micro.log)
-  pl.smem = fixed + pl.y_bytes + N_A * pl.a_stage + pl.b_stages * B_BYTES;
+  if (pl.b_stages < 4) return pl;                                // with 3 weight stages the kernel was 7 % SLOWER than the two GEMM launches (profiles/r2_tcn_block_micro.log)
+  pl.smem = fixed + pl.tiles_bytes + pl.b_stages * B_BYTES;
   pl.ok = true;
   return pl;
 }
@@ -410,12 +423,11 @@ cudaError_t launch_tcn_block(void* encode_fn, int num_sms, const TcnBlock& t, cu
   CUtensorMap m_h, m_w1, m_w2, m_out;
   cuuint32_t es3[3] = {1, 1, 1}, es2[2] = {1, 1};
   const int64_t W = t.M / t.T;
-  const int pad = 2 * t.dil;
   {
     // activations as (channel, window, frame): the box (64, NW, T + 4 dil) starts at frame -2 dil; out-of-bounds frames are zero fill
     cuuint64_t gdim[3] = {(cuuint64_t)BN, (cuuint64_t)W, (cuuint64_t)t.T};
     cuuint64_t gstr[2] = {(cuuint64_t)t.T * BN * 2, (cuuint64_t)BN * 2};
-    cuuint32_t box[3] = {BK, (cuuint32_t)pl.nw, (cuuint32_t)(t.T + 2 * pad)};
+    cuuint32_t box[3] = {BK, (cuuint32_t)pl.nw, (cuuint32_t)(pl.a_box_rows / pl.nw)};
     CUresult r = encode(&m_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, t.h16, gdim, gstr, box, es3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(h) failed with CUresult %d", (int)r); return cudaErrorInvalidValue; }
@@ -440,7 +452,8 @@ cudaError_t launch_tcn_block(void* encode_fn, int num_sms, const TcnBlock& t, cu
   p.M = t.M; p.m_tiles = (t.M + BM - 1) / BM;
   p.T = t.T; p.lw = pl.nw > 1 ? pl.lw : 0; p.lt = pl.lt; p.nw = pl.nw;
   p.dil = t.dil; p.tap_rows = t.dil * pl.nw; p.halo_rows = pl.halo_rows;
-  p.y_sub_bytes = pl.y_sub; p.y_bytes = pl.y_bytes; p.a_stage_bytes = pl.a_stage; p.a_box_bytes = pl.y_rows * 128; p.stg_off = pl.stg_off; p.b_stages = pl.b_stages;
+  p.y_sub_bytes = pl.y_sub; p.a_ring_off = pl.a_ring_off; p.a_stage_bytes = pl.a_stage; p.a_dst_off = pl.a_dst_off; p.a_ct = pl.a_ct;
+  p.a_box_bytes = pl.a_box_rows * 128; p.tiles_bytes = pl.tiles_bytes; p.stg_off = pl.stg_off; p.b_stages = pl.b_stages;
   p.gn_gamma = t.gn_gamma; p.gn_beta = t.gn_beta; p.res16 = t.h16; p.ldr = BN;
   const int64_t total = (p.m_tiles + 1) / 2;
   const int64_t clusters = total < num_sms / 2 ? total : num_sms / 2;
