@@ -230,6 +230,9 @@ int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x1
  * dilation whose halo tile does not fit next to the weight ring (T = 32: dilation 8). Bit-identical to that path. */
 int tag_debug_tcn_block(tag_handle* h, void* h16, int64_t M, int32_t T, int32_t dil, const void* W1_16, const void* W2_16,
                         const float* gn_gamma, const float* gn_beta, void* stream);
+/* host-only: 1 if the fused block kernel covers (M rows, T frames per window, dilation), with its shared-memory plan: weight-ring
+ * stages, dynamic shared memory of the launch, bytes of the six activation tiles and their zero halos. No GPU needed. */
+int tag_debug_tcn_block_plan(int64_t M, int32_t T, int32_t dil, int32_t* weight_stages, int32_t* smem_bytes, int32_t* tile_bytes);
 
 #ifdef __cplusplus
 }

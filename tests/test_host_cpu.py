@@ -29,6 +29,33 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert tb.load_library().tag_abi_version() == 2
 
 
+def test_fused_conv_block_shared_memory_plan():
+    """Host-side plan of the fused TemporalConvBlock kernel (csrc/tcn_block_tc.cu): six 128-row tiles between shared zero halos of
+    2 * dil * (128 / T) rows, then the weight ring — at least four 16 KB stages inside the 227 KB a CTA may use, else the shape stays on
+    the two-kernel path."""
+    lib = tb.load_library()
+    ws, sm, tl = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+
+    def plan(M, T, dil):
+        ok = lib.tag_debug_tcn_block_plan(M, T, dil, ctypes.byref(ws), ctypes.byref(sm), ctypes.byref(tl))
+        return ok, ws.value, sm.value, tl.value
+
+    for dil, stages in ((1, 7), (2, 6), (4, 5), (8, 4)):                      # config 2: T = 32, four windows per tile
+        ok, w, smem, tiles = plan(400000, 32, dil)
+        halo = 2 * dil * 4
+        assert ok == 1 and w == stages
+        assert tiles == (6 * (halo + 128) + halo) * 128                      # multiples of 1024 here: every tile on a swizzle-atom boundary
+        assert smem <= 232448 and smem >= tiles + w * 16384
+    assert plan(400000, 32, 16)[0] == 0                                      # halo tiles leave no room for the weight ring
+    assert plan(400000, 16, 8)[0] == 0
+    assert plan(131072, 256, 1)[0] == 0                                      # a window spans two tiles
+    assert plan(2400, 24, 1)[0] == 0                                         # not a power of two
+    assert plan(128, 32, 1)[0] == 0 and plan(160, 32, 1)[0] == 1             # a single tile has no CTA pair
+    assert plan(1000, 32, 1)[0] == 0                                         # rows must be whole windows
+    ok, w, smem, tiles = plan(12800, 128, 1)                                 # halo of 2 rows: unshared layout, TMA zero fill writes the halos
+    assert ok == 1 and w >= 4 and tiles % 1024 == 0 and smem <= 232448
+
+
 def test_config_struct_layout_matches_header():
     # 3 arrays of 8 + 1 + 10 scalars, all int32
     assert ctypes.sizeof(_lib.tag_config) == 4 * (1 + 3 * 8 + 10)

@@ -71,6 +71,7 @@ SIGNATURES = {
     "tag_debug_poison_workspace": (C.c_int, [_P, _P]),
     "tag_debug_tlayer_tail": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tag_debug_tcn_block": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
+    "tag_debug_tcn_block_plan": (C.c_int, [_I64, _I32, _I32, _P, _P, _P]),
     "tag_debug_gemm_tc": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
 }
 

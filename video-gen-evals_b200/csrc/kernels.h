@@ -157,6 +157,7 @@ struct TcnBlock {
   const float* gn_gamma; const float* gn_beta;
 };
 bool tcn_block_supported(int64_t M, int T, int dil);
+bool tcn_block_plan(int64_t M, int T, int dil, int* weight_stages, int* smem_bytes, int* tile_bytes);   // host only
 cudaError_t launch_tcn_block(void* encode_fn, int num_sms, const TcnBlock& t, cudaStream_t s, char* err, int errlen);
 
 // ------------------------------------------------------------------ fused transformer-layer tail (tlayer_tc.cu)

@@ -1193,6 +1193,15 @@ int tag_debug_tlayer_tail(tag_handle* h, const void* att16, float* x32, void* x1
   return TAG_OK;
 }
 
+int tag_debug_tcn_block_plan(int64_t M, int32_t T, int32_t dil, int32_t* weight_stages, int32_t* smem_bytes, int32_t* tile_bytes) {
+  int ws = 0, sb = 0, tb = 0;
+  const bool ok = tcn_block_plan(M, T, dil, &ws, &sb, &tb);
+  if (weight_stages) *weight_stages = ws;
+  if (smem_bytes) *smem_bytes = sb;
+  if (tile_bytes) *tile_bytes = tb;
+  return ok ? 1 : 0;
+}
+
 int tag_debug_tcn_block(tag_handle* h, void* h16, int64_t M, int32_t T, int32_t dil, const void* W1_16, const void* W2_16,
                         const float* gn_gamma, const float* gn_beta, void* stream) {
   if (!h) return TAG_ERR_INVALID;

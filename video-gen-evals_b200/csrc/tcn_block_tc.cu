@@ -400,6 +400,15 @@ Plan make_plan(int64_t M, int T, int dil) {
 
 bool tcn_block_supported(int64_t M, int T, int dil) { return make_plan(M, T, dil).ok; }
 
+// host-only view of the shared-memory plan (tag_debug_tcn_block_plan: lets the CPU test suite pin the budget arithmetic)
+bool tcn_block_plan(int64_t M, int T, int dil, int* weight_stages, int* smem_bytes, int* tile_bytes) {
+  const Plan pl = make_plan(M, T, dil);
+  if (weight_stages) *weight_stages = pl.ok ? pl.b_stages : 0;
+  if (smem_bytes) *smem_bytes = pl.ok ? pl.smem : 0;
+  if (tile_bytes) *tile_bytes = pl.ok ? pl.tiles_bytes : 0;
+  return pl.ok;
+}
+
 cudaError_t launch_tcn_block(void* encode_fn, int num_sms, const TcnBlock& t, cudaStream_t s, char* err, int errlen) {
   if (t.M <= 0) return cudaSuccess;
   auto bad = [&](const char* msg) {
