@@ -13,8 +13,9 @@ videos are sharded across ranks with no data-path collective.
   e2e    : same metric through the public streaming call (TagScorer.score_stream) with HOST (pinned)
            input buffers: every step's H2D of all input arrays (copy stream, prefetched across step
            boundaries) + scoring + D2H of the per-video results, all inside the timed region
-  roofline: dominant kernel = the dilated-conv tensor-core GEMM; achieved = algorithmic FLOPs per launch
-           / mean launch duration measured with CUDA events on the launching stream during the timed
+  roofline: dominant kernel = the dilated-conv blocks on tcgen05 (k_tcn_block: a fused TemporalConvBlock, 2 convs per
+           launch; k_gemm_tc where a shape takes the two-kernel path); achieved = algorithmic FLOPs of those launches
+           / their total duration measured with CUDA events on the launching stream during the timed
            steps; peak = MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)
   hbm_kernels: the bandwidth-bound kernels (K1, merge-fusion, attention, build-tokens, finalize+TC, K3, K4):
            algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json hbm_gbs
